@@ -1,0 +1,154 @@
+// Small kernels around the hot path: weight repacking, deterministic cross-CTA
+// reduction, data-term seeds, TF-1 Adam, Philox collocation sampler.
+#include "pinn_kernels.h"
+
+namespace {
+
+// theta -> zero-padded Wp_l [n_in][np_out] and transposed WT_l [n_out][np_in]
+__global__ void repack_kernel(const NetDesc net, const float* __restrict__ theta, float* __restrict__ wp,
+                              float* __restrict__ wt) {
+  const int l = blockIdx.y;
+  const int n_in = net.n[l], n_out = net.n[l + 1], np_in = net.np[l], np_out = net.np[l + 1];
+  const float* W = theta + net.w_off[l];
+  float* Wp = wp + net.wp_off[l];
+  float* WT = wt + net.wt_off[l];
+  const int tot1 = n_in * np_out, tot2 = n_out * np_in;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < tot1 + tot2; k += gridDim.x * blockDim.x) {
+    if (k < tot1) {
+      const int i = k / np_out, j = k % np_out;
+      Wp[k] = (j < n_out) ? W[i * n_out + j] : 0.f;
+    } else {
+      const int kk = k - tot1;
+      const int j = kk / np_in, i = kk % np_in;
+      WT[kk] = (i < n_in) ? W[i * n_out + j] : 0.f;
+    }
+  }
+}
+
+// packed[k] (+)= sum over CTA rows, fixed order, double accumulation -> run-to-run reproducible
+__global__ void finalize_kernel(const float* __restrict__ part, int nrows, int rvlen, float* __restrict__ packed,
+                                int accumulate, const float* __restrict__ extra, int extra_idx) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= rvlen) return;
+  double s = 0.0;
+  for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * rvlen + k];
+  if (extra != nullptr && k == extra_idx) s += (double)extra[0];
+  packed[k] = accumulate ? (float)((double)packed[k] + s) : (float)s;
+}
+
+// data misfit r = u - u^, its loss and the adjoints dL/du^ (appendix A.3):
+//   V1 (INF-L2:68): ||r||_2 -> -r/||r||      others: (1/N_u)||r||^2 -> -2 r / N_u
+__global__ void data_seed_kernel(const float* __restrict__ u_pred, const float* __restrict__ u_data, int64_t n, int loss,
+                                 float weight, float* __restrict__ seed, float* __restrict__ loss_out, int64_t n_u) {
+  __shared__ double red[32];
+  __shared__ double total;
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const float r = u_data[k] - u_pred[k];
+    s += (double)r * (double)r;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    total = t;
+  }
+  __syncthreads();
+  const double ss = total;
+  float scale;
+  if (loss == PINN_LOSS_V1_INF_L2) {
+    const float nr = sqrtf((float)ss);
+    scale = -weight / nr;  // NaN at exactly zero misfit, as tf.norm's gradient is
+    if (threadIdx.x == 0) loss_out[0] = weight * nr;
+  } else {
+    scale = -2.0f * weight / (float)n_u;
+    if (threadIdx.x == 0) loss_out[0] = weight * (float)(ss / (double)n_u);
+  }
+  for (int64_t k = threadIdx.x; k < n; k += blockDim.x) seed[k] = scale * (u_data[k] - u_pred[k]);
+}
+
+// tf.train.AdamOptimizer (TF-1 ApplyAdam, appendix A.4): epsilon outside the bias correction
+__global__ void adam_prep_kernel(double* scal, float lr, float beta1, float beta2) {
+  const double t = scal[0] + 1.0;
+  const double b1p = scal[1] * (double)beta1, b2p = scal[2] * (double)beta2;
+  scal[0] = t;
+  scal[1] = b1p;
+  scal[2] = b2p;
+  scal[3] = (double)lr * sqrt(1.0 - b2p) / (1.0 - b1p);
+}
+
+__global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                            float* __restrict__ v, const double* __restrict__ scal, int n, float beta1, float beta2,
+                            float eps) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float alpha = (float)scal[3];
+  const float g = grad[k];
+  float mk = m[k], vk = v[k];
+  mk += (g - mk) * (1.0f - beta1);
+  vk += (g * g - vk) * (1.0f - beta2);
+  m[k] = mk;
+  v[k] = vk;
+  theta[k] -= (mk * alpha) / (sqrtf(vk) + eps);
+}
+
+__global__ void sample_kernel(float* __restrict__ X, int64_t n, uint64_t seed, uint64_t first, float lbx, float lbt,
+                              float spanx, float spant) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = first + (uint64_t)i;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    const float u0 = (float)(o[0] >> 8) * 5.9604644775390625e-08f;  // 2^-24, [0,1)
+    const float u1 = (float)(o[1] >> 8) * 5.9604644775390625e-08f;
+    float2 xt;
+    xt.x = fmaf(spanx, u0, lbx);
+    xt.y = fmaf(spant, u1, lbt);
+    *reinterpret_cast<float2*>(X + 2 * i) = xt;
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+cudaError_t pinn_repack_launch(const NetDesc& net, const float* theta, float* wp, float* wt, cudaStream_t stream) {
+  dim3 grid(32, net.L);
+  repack_kernel<<<grid, 256, 0, stream>>>(net, theta, wp, wt);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_finalize_launch(const float* part, int nrows, int rvlen, float* packed, int accumulate, const float* extra,
+                                 int extra_idx, cudaStream_t stream) {
+  finalize_kernel<<<(rvlen + 127) / 128, 128, 0, stream>>>(part, nrows, rvlen, packed, accumulate, extra, extra_idx);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_data_seed_launch(const float* u_pred, const float* u_data, int64_t n_u, int n_out, int loss, float weight,
+                                  float* seed, float* loss_out, cudaStream_t stream) {
+  data_seed_kernel<<<1, 1024, 0, stream>>>(u_pred, u_data, n_u * n_out, loss, weight, seed, loss_out, n_u);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, int n, float lr, float beta1, float beta2,
+                             float eps, cudaStream_t stream) {
+  adam_prep_kernel<<<1, 1, 0, stream>>>(st.scal, lr, beta1, beta2);
+  adam_kernel<<<(n + 255) / 256, 256, 0, stream>>>(theta, packed, st.m, st.v, st.scal, n, beta1, beta2, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_sample_launch(float* X, int64_t n, uint64_t seed, uint64_t first_index, float lbx, float lbt, float spanx,
+                               float spant, cudaStream_t stream) {
+  const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  sample_kernel<<<grid > 0 ? grid : 1, 256, 0, stream>>>(X, n, seed, first_index, lbx, lbt, spanx, spant);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_fill_launch(float* p, int64_t n, float v, cudaStream_t stream) {
+  const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  fill_kernel<<<grid > 0 ? grid : 1, 256, 0, stream>>>(p, n, v);
+  return cudaGetLastError();
+}

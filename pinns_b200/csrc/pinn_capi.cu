@@ -1,0 +1,761 @@
+// C ABI of libpinn_b200.so (see include/pinn_b200.h for the contract and the reference
+// lines each entry point replaces).  Host-side orchestration only: every FLOP of the hot
+// path runs in the sm_100a kernels of pinn_fused.cu / pinn_generic.cu; there is no CPU path.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "pinn_kernels.h"
+#include "pinn_fused.h"
+
+struct pinn_handle_s {
+  pinn_config_t cfg;
+  NetDesc net;
+  int S_res = 4;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  int path_used = PINN_PATH_GENERIC;
+
+  float* d_theta = nullptr;  // [P+2]
+  float* d_wp = nullptr;
+  float* d_wt = nullptr;
+  bool weights_dirty = true;
+  int rvlen = 0;
+  float* d_packed = nullptr;
+
+  float* d_Xu = nullptr;
+  float* d_u = nullptr;
+  float* d_upred = nullptr;
+  float* d_seed = nullptr;
+  float* d_data_loss = nullptr;
+  int64_t n_u = 0;
+  float data_weight = 1.0f;
+
+  float* d_Xf = nullptr;
+  float* d_Xf_owned = nullptr;
+  int64_t xf_cap = 0;
+  int64_t n_f = 0, nf_global = 0;
+  float* d_z = nullptr;
+  float* d_gamma = nullptr;
+  int64_t admm_cap = 0;
+
+  AdamState adam = {nullptr, nullptr, nullptr};
+  float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+
+  float* d_scratch = nullptr;
+  int gen_grid_max = 0;
+  float* d_part = nullptr;
+  float* d_part_data = nullptr;
+  ScratchDesc sd_res, sd_data;
+  float* d_l1sum = nullptr;
+  bool l1_ready = false;
+
+  FusedState fused;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                                 \
+      return PINN_E_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define REQUIRE(cond, code, msg) \
+  do {                           \
+    if (!(cond)) {               \
+      h->err = (msg);            \
+      return (code);             \
+    }                            \
+  } while (0)
+
+static int round8(int v) { return (v + 7) / 8 * 8; }
+
+static ScratchDesc make_scratch_desc(const NetDesc& net, int S) {
+  ScratchDesc sd;
+  memset(&sd, 0, sizeof(sd));
+  int off = 0;
+  sd.in0 = off;
+  off += S * 8 * PINN_TILE;
+  for (int hl = 0; hl < net.L - 1; ++hl) {
+    sd.hid[hl] = off;
+    off += (2 * S - 1) * net.np[hl + 1] * PINN_TILE;
+  }
+  sd.Y = off;
+  off += S * 8 * PINN_TILE;
+  for (int k = 0; k < 2; ++k) {
+    sd.zb[k] = off;
+    off += S * net.npmax * PINN_TILE;
+  }
+  sd.total = off;
+  return sd;
+}
+
+static LossCoef make_loss_coef(const pinn_handle_s* h, int loss) {
+  LossCoef lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.loss = loss;
+  lc.rho = h->cfg.rho;
+  const double nf = (double)(h->nf_global > 0 ? h->nf_global : (h->n_f > 0 ? h->n_f : 1));
+  lc.inv_nf = (float)(1.0 / nf);
+  switch (loss) {
+    case PINN_LOSS_V1_INF_L2:
+    case PINN_LOSS_V4_MSE:
+      lc.cA = (float)(2.0 / nf);
+      break;
+    case PINN_LOSS_V3_L1SQ:
+      break;  // cB formed on the device from the job-wide sum |f|
+    case PINN_LOSS_V5_ADMM:
+      lc.cC = h->cfg.rho;
+      lc.cD = 1.0f;
+      break;
+    case PINN_LOSS_V2_INF_ADMM:
+      lc.cC = h->cfg.rho;
+      lc.cD = 2.0f;
+      break;
+  }
+  return lc;
+}
+
+static int ensure_weights(pinn_handle_t h) {
+  if (h->weights_dirty) {
+    CK(pinn_repack_launch(h->net, h->d_theta, h->d_wp, h->d_wt, h->stream));
+    h->launches += 1;
+    h->weights_dirty = false;
+  }
+  return PINN_OK;
+}
+
+static int gen_grid_for(const pinn_handle_s* h, int64_t n) {
+  const int64_t tiles = (n + PINN_TILE - 1) / PINN_TILE;
+  return (int)(tiles < h->gen_grid_max ? (tiles > 0 ? tiles : 1) : h->gen_grid_max);
+}
+
+// one launch of the generic kernel; returns the grid used through *grid_out
+static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
+                       float* u_out, float* f_out, int admm_op, bool use_state, float* part, int* grid_out) {
+  GenParams g;
+  memset(&g, 0, sizeof(g));
+  g.net = h->net;
+  g.lc = make_loss_coef(h, loss);
+  g.sd = (S == 1) ? h->sd_data : h->sd_res;
+  g.theta = h->d_theta;
+  g.wp = h->d_wp;
+  g.wt = h->d_wt;
+  g.X = X;
+  g.N = n;
+  g.nf_global = h->nf_global > 0 ? h->nf_global : h->n_f;
+  g.mode = mode;
+  g.seed = seed;
+  g.l1_sum = (loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr;
+  g.u_out = u_out;
+  g.f_out = f_out;
+  g.z = use_state ? h->d_z : nullptr;
+  g.gamma = use_state ? h->d_gamma : nullptr;
+  g.admm_op = admm_op;
+  g.scratch = h->d_scratch;
+  g.part = part;
+  g.rvlen = h->rvlen;
+  const int grid = gen_grid_for(h, n);
+  CK(pinn_generic_launch(g, S, grid, h->stream));
+  h->launches += 1;
+  if (grid_out) *grid_out = grid;
+  return PINN_OK;
+}
+
+static bool loss_uses_state(int loss) { return loss == PINN_LOSS_V2_INF_ADMM || loss == PINN_LOSS_V5_ADMM; }
+
+static int ensure_admm(pinn_handle_t h) {
+  const int64_t need = h->n_f * h->net.n_res;
+  if (need > h->admm_cap) {
+    if (h->d_z) cudaFree(h->d_z);
+    if (h->d_gamma) cudaFree(h->d_gamma);
+    h->d_z = h->d_gamma = nullptr;
+    CK(cudaMalloc(&h->d_z, need * sizeof(float)));
+    CK(cudaMalloc(&h->d_gamma, need * sizeof(float)));
+    h->admm_cap = need;
+    CK(pinn_fill_launch(h->d_z, need, 1.0f, h->stream));  // tf.ones (AB-ADMM:121-122)
+    CK(pinn_fill_launch(h->d_gamma, need, 1.0f, h->stream));
+    h->launches += 2;
+  }
+  return PINN_OK;
+}
+
+extern "C" {
+
+const char* pinn_last_error(pinn_handle_t h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int pinn_create(const pinn_config_t* cfg, pinn_handle_t* out) {
+  if (!cfg || !out) {
+    g_create_err = "pinn_create: null argument";
+    return PINN_E_INVALID;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != PINN_B200_ABI_VERSION) {
+    g_create_err = "pinn_create: abi_version mismatch";
+    return PINN_E_INVALID;
+  }
+  if (cfg->n_layers < 3 || cfg->n_layers > PINN_MAX_LAYERS || cfg->layers[0] != 2) {
+    g_create_err = "pinn_create: need 3..16 layers with layers[0] == 2 (x,t)";
+    return PINN_E_INVALID;
+  }
+  const int n_out = cfg->layers[cfg->n_layers - 1];
+  if ((cfg->pde == PINN_PDE_BURGERS && n_out != 1) || (cfg->pde == PINN_PDE_EULER && n_out != 3) ||
+      (cfg->pde != PINN_PDE_BURGERS && cfg->pde != PINN_PDE_EULER)) {
+    g_create_err = "pinn_create: Burgers needs 1 output, Euler needs 3 (rho,u,E)";
+    return PINN_E_INVALID;
+  }
+  if (cfg->loss < PINN_LOSS_V1_INF_L2 || cfg->loss > PINN_LOSS_V5_ADMM) {
+    g_create_err = "pinn_create: unknown loss variant";
+    return PINN_E_INVALID;
+  }
+  for (int l = 0; l < cfg->n_layers; ++l)
+    if (cfg->layers[l] < 1 || cfg->layers[l] > 1024) {
+      g_create_err = "pinn_create: layer width out of range [1,1024]";
+      return PINN_E_INVALID;
+    }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("pinn_create: no CUDA device (") + cudaGetErrorString(e) + "); libpinn_b200 has no CPU path";
+    return PINN_E_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_err = "pinn_create: device ordinal out of range";
+    return PINN_E_INVALID;
+  }
+  pinn_handle_s* h = new (std::nothrow) pinn_handle_s();
+  if (!h) {
+    g_create_err = "pinn_create: out of host memory";
+    return PINN_E_NOMEM;
+  }
+  h->cfg = *cfg;
+  NetDesc& net = h->net;
+  memset(&net, 0, sizeof(net));
+  net.L = cfg->n_layers - 1;
+  int off = 0, wp = 0, wt = 0, npmax = 8;
+  for (int l = 0; l <= net.L; ++l) {
+    net.n[l] = cfg->layers[l];
+    net.np[l] = round8(cfg->layers[l]);
+    if (l > 0 && net.np[l] > npmax) npmax = net.np[l];
+  }
+  for (int l = 0; l < net.L; ++l) {
+    net.w_off[l] = off;
+    off += net.n[l] * net.n[l + 1];
+    net.b_off[l] = off;
+    off += net.n[l + 1];
+    net.wp_off[l] = wp;
+    wp += net.n[l] * net.np[l + 1];
+    net.wt_off[l] = wt;
+    wt += net.n[l + 1] * net.np[l];
+  }
+  net.P = off;
+  net.npmax = npmax;
+  net.n_out = n_out;
+  net.n_res = cfg->pde == PINN_PDE_BURGERS ? 1 : 3;
+  net.pde = cfg->pde;
+  net.lbx = (float)cfg->lb[0];
+  net.lbt = (float)cfg->lb[1];
+  net.spanx = (float)(cfg->ub[0] - cfg->lb[0]);
+  net.spant = (float)(cfg->ub[1] - cfg->lb[1]);
+  h->S_res = cfg->pde == PINN_PDE_BURGERS ? 4 : 3;
+  h->rvlen = net.P + 2 + PINN_NSUMS;
+
+  auto fail = [&](const char* what, cudaError_t ce) {
+    g_create_err = std::string("pinn_create: ") + what + ": " + cudaGetErrorString(ce);
+    pinn_destroy(h);
+    return PINN_E_CUDA;
+  };
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  if (prop.major != 10) {
+    g_create_err = "pinn_create: libpinn_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor) + ")";
+    pinn_destroy(h);
+    return PINN_E_INVALID;
+  }
+  h->num_sms = prop.multiProcessorCount;
+  h->gen_grid_max = h->num_sms * 2;
+  h->sd_res = make_scratch_desc(net, h->S_res);
+  h->sd_data = make_scratch_desc(net, 1);
+
+  const size_t px = (size_t)net.P + 2;
+  if ((e = cudaMalloc(&h->d_theta, px * sizeof(float))) != cudaSuccess) return fail("cudaMalloc theta", e);
+  if ((e = cudaMemset(h->d_theta, 0, px * sizeof(float))) != cudaSuccess) return fail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->d_wp, (size_t)wp * sizeof(float))) != cudaSuccess) return fail("cudaMalloc wp", e);
+  if ((e = cudaMalloc(&h->d_wt, (size_t)wt * sizeof(float))) != cudaSuccess) return fail("cudaMalloc wt", e);
+  if ((e = cudaMalloc(&h->d_packed, (size_t)h->rvlen * sizeof(float))) != cudaSuccess) return fail("cudaMalloc packed", e);
+  if ((e = cudaMemset(h->d_packed, 0, (size_t)h->rvlen * sizeof(float))) != cudaSuccess) return fail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->d_scratch, (size_t)h->sd_res.total * h->gen_grid_max * sizeof(float))) != cudaSuccess)
+    return fail("cudaMalloc scratch", e);
+  if ((e = cudaMalloc(&h->d_part, (size_t)h->rvlen * h->gen_grid_max * sizeof(float))) != cudaSuccess)
+    return fail("cudaMalloc partials", e);
+  if ((e = cudaMalloc(&h->d_part_data, (size_t)h->rvlen * h->gen_grid_max * sizeof(float))) != cudaSuccess)
+    return fail("cudaMalloc data partials", e);
+  if ((e = cudaMalloc(&h->d_l1sum, sizeof(float))) != cudaSuccess) return fail("cudaMalloc l1", e);
+  if ((e = cudaMalloc(&h->d_data_loss, sizeof(float))) != cudaSuccess) return fail("cudaMalloc dl", e);
+  if ((e = cudaMemset(h->d_data_loss, 0, sizeof(float))) != cudaSuccess) return fail("cudaMemset", e);
+  if ((e = cudaMalloc(&h->adam.m, px * sizeof(float))) != cudaSuccess) return fail("cudaMalloc m", e);
+  if ((e = cudaMalloc(&h->adam.v, px * sizeof(float))) != cudaSuccess) return fail("cudaMalloc v", e);
+  if ((e = cudaMalloc(&h->adam.scal, 4 * sizeof(double))) != cudaSuccess) return fail("cudaMalloc adam scal", e);
+  *out = h;
+  int rc = pinn_adam_reset(h);
+  if (rc != PINN_OK) {
+    g_create_err = h->err;
+    pinn_destroy(h);
+    *out = nullptr;
+    return rc;
+  }
+  rc = pinn_set_lambda(h, cfg->lambda1, cfg->lambda2);
+  if (rc == PINN_OK) rc = fused_init(h->fused, h->net, h->cfg, h->num_sms, h->rvlen, h->err);
+  if (rc != PINN_OK) {
+    g_create_err = h->err;
+    pinn_destroy(h);
+    *out = nullptr;
+    return rc;
+  }
+  h->path_used = h->fused.enabled ? PINN_PATH_FUSED : PINN_PATH_GENERIC;
+  return PINN_OK;
+}
+
+int pinn_destroy(pinn_handle_t h) {
+  if (!h) return PINN_OK;
+  cudaSetDevice(h->cfg.device);
+  fused_destroy(h->fused);
+  float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
+                   h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
+                   h->d_l1sum, h->d_data_loss};
+  for (float* b : bufs)
+    if (b) cudaFree(b);
+  if (h->adam.scal) cudaFree(h->adam.scal);
+  delete h;
+  return PINN_OK;
+}
+
+int pinn_set_stream(pinn_handle_t h, void* s) {
+  if (!h) return PINN_E_INVALID;
+  h->stream = (cudaStream_t)s;
+  return PINN_OK;
+}
+
+int pinn_synchronize(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_num_params(pinn_handle_t h, int64_t* n) {
+  if (!h || !n) return PINN_E_INVALID;
+  *n = h->net.P;
+  return PINN_OK;
+}
+int pinn_packed_len(pinn_handle_t h, int64_t* n) {
+  if (!h || !n) return PINN_E_INVALID;
+  *n = h->rvlen;
+  return PINN_OK;
+}
+int pinn_kernel_path(pinn_handle_t h, int32_t* p) {
+  if (!h || !p) return PINN_E_INVALID;
+  *p = h->path_used;
+  return PINN_OK;
+}
+int pinn_launch_count(pinn_handle_t h, int64_t* n) {
+  if (!h || !n) return PINN_E_INVALID;
+  *n = h->launches;
+  return PINN_OK;
+}
+
+int pinn_set_params(pinn_handle_t h, const float* theta, int on_device) {
+  if (!h || !theta) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->d_theta, theta, (size_t)h->net.P * sizeof(float),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  h->weights_dirty = true;
+  return PINN_OK;
+}
+
+int pinn_get_params(pinn_handle_t h, float* theta, int on_device) {
+  if (!h || !theta) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(theta, h->d_theta, (size_t)h->net.P * sizeof(float),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_set_lambda(pinn_handle_t h, float l1, float l2) {
+  if (!h) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  const float v[2] = {l1, l2};
+  CK(cudaMemcpyAsync(h->d_theta + h->net.P, v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_get_lambda(pinn_handle_t h, float* l1, float* l2) {
+  if (!h || !l1 || !l2) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  float v[2];
+  CK(cudaMemcpyAsync(v, h->d_theta + h->net.P, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *l1 = v[0];
+  *l2 = v[1];
+  return PINN_OK;
+}
+
+int pinn_set_data(pinn_handle_t h, const float* X_u, const float* u, int64_t n_u, int on_device) {
+  if (!h || n_u < 0 || (n_u > 0 && (!X_u || !u))) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  float** bufs[] = {&h->d_Xu, &h->d_u, &h->d_upred, &h->d_seed};
+  for (float** b : bufs) {
+    if (*b) cudaFree(*b);
+    *b = nullptr;
+  }
+  h->n_u = n_u;
+  if (n_u == 0) return PINN_OK;
+  const size_t no = (size_t)h->net.n_out;
+  CK(cudaMalloc(&h->d_Xu, (size_t)n_u * 2 * sizeof(float)));
+  CK(cudaMalloc(&h->d_u, (size_t)n_u * no * sizeof(float)));
+  CK(cudaMalloc(&h->d_upred, (size_t)n_u * no * sizeof(float)));
+  CK(cudaMalloc(&h->d_seed, (size_t)n_u * no * sizeof(float)));
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpyAsync(h->d_Xu, X_u, (size_t)n_u * 2 * sizeof(float), k, h->stream));
+  CK(cudaMemcpyAsync(h->d_u, u, (size_t)n_u * no * sizeof(float), k, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+static int ensure_xf_owned(pinn_handle_t h, int64_t n_f) {
+  if (n_f > h->xf_cap) {
+    if (h->d_Xf_owned) cudaFree(h->d_Xf_owned);
+    h->d_Xf_owned = nullptr;
+    CK(cudaMalloc(&h->d_Xf_owned, (size_t)n_f * 2 * sizeof(float)));
+    h->xf_cap = n_f;
+  }
+  return PINN_OK;
+}
+
+int pinn_set_collocation(pinn_handle_t h, const float* X_f, int64_t n_f, int64_t nf_global, int on_device) {
+  if (!h || !X_f || n_f <= 0) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (on_device) {
+    h->d_Xf = const_cast<float*>(X_f);  // borrowed
+  } else {
+    int rc = ensure_xf_owned(h, n_f);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_Xf_owned, X_f, (size_t)n_f * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->d_Xf = h->d_Xf_owned;
+  }
+  h->n_f = n_f;
+  h->nf_global = nf_global > 0 ? nf_global : n_f;
+  h->l1_ready = false;
+  return PINN_OK;
+}
+
+int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index, int64_t n_f, int64_t nf_global) {
+  if (!h || n_f <= 0) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_xf_owned(h, n_f);
+  if (rc) return rc;
+  CK(pinn_sample_launch(h->d_Xf_owned, n_f, seed, first_index, h->net.lbx, h->net.lbt, h->net.spanx, h->net.spant,
+                        h->stream));
+  h->launches += 1;
+  h->d_Xf = h->d_Xf_owned;
+  h->n_f = n_f;
+  h->nf_global = nf_global > 0 ? nf_global : n_f;
+  h->l1_ready = false;
+  return PINN_OK;
+}
+
+int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device) {
+  if (!h || !X_f) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_get_collocation: no collocation points set");
+  CK(cudaMemcpyAsync(X_f, h->d_Xf, (size_t)h->n_f * 2 * sizeof(float),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_set_data_weight(pinn_handle_t h, float w) {
+  if (!h) return PINN_E_INVALID;
+  h->data_weight = w;
+  return PINN_OK;
+}
+
+// data term: forward on X_u, misfit + adjoints, seeded reverse sweep (primal stream only)
+static int data_term(pinn_handle_t h, bool want_grad) {
+  if (h->n_u == 0 || h->data_weight == 0.0f) {
+    CK(cudaMemsetAsync(h->d_data_loss, 0, sizeof(float), h->stream));
+    return PINN_OK;
+  }
+  int rc = run_generic(h, 1, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, nullptr, h->d_upred, nullptr, 0, false,
+                       h->d_part_data, nullptr);
+  if (rc) return rc;
+  CK(pinn_data_seed_launch(h->d_upred, h->d_u, h->n_u, h->net.n_out, h->cfg.loss, h->data_weight, h->d_seed,
+                           h->d_data_loss, h->stream));
+  h->launches += 1;
+  if (want_grad) {
+    int grid = 0;
+    rc = run_generic(h, 1, GEN_MODE_TRAIN, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, h->d_seed, nullptr, nullptr, 0, false,
+                     h->d_part_data, &grid);
+    if (rc) return rc;
+    CK(pinn_finalize_launch(h->d_part_data, grid, h->rvlen, h->d_packed, 1, h->d_data_loss, h->net.P + 2 + PINN_SUM_DATA,
+                            h->stream));
+    h->launches += 1;
+  }
+  return PINN_OK;
+}
+
+static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
+  const bool state = loss_uses_state(h->cfg.loss) || admm_op != 0;
+  if (state) {
+    int rc = ensure_admm(h);
+    if (rc) return rc;
+  }
+  if (h->fused.enabled) {
+    int rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
+                       h->nf_global > 0 ? h->nf_global : h->n_f, mode,
+                       (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
+                       state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, h->d_packed, h->stream, h->err);
+    if (rc) return rc;
+    h->launches += 2;
+    return PINN_OK;
+  }
+  int grid = 0;
+  int rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state,
+                       h->d_part, &grid);
+  if (rc) return rc;
+  CK(pinn_finalize_launch(h->d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
+  h->launches += 1;
+  return PINN_OK;
+}
+
+int pinn_l1_pass1(pinn_handle_t h, float** dev_sum) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_l1_pass1: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  rc = residual_pass(h, GEN_MODE_FORWARD, 0);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_l1sum, h->d_packed + h->net.P + 2 + PINN_SUM_ABSF, sizeof(float), cudaMemcpyDeviceToDevice,
+                     h->stream));
+  h->l1_ready = true;
+  if (dev_sum) *dev_sum = h->d_l1sum;
+  return PINN_OK;
+}
+
+int pinn_loss_grad_device(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_loss_grad: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  if (h->cfg.loss == PINN_LOSS_V3_L1SQ && !h->l1_ready) {
+    rc = pinn_l1_pass1(h, nullptr);
+    if (rc) return rc;
+  }
+  rc = residual_pass(h, GEN_MODE_TRAIN, 0);
+  if (rc) return rc;
+  h->l1_ready = false;
+  return data_term(h, true);
+}
+
+int pinn_packed_ptr(pinn_handle_t h, float** p) {
+  if (!h || !p) return PINN_E_INVALID;
+  *p = h->d_packed;
+  return PINN_OK;
+}
+
+static double assemble_loss(const pinn_handle_s* h, const float* sums) {
+  const double nf = (double)(h->nf_global > 0 ? h->nf_global : h->n_f);
+  double loss = (double)sums[PINN_SUM_DATA];
+  if (h->cfg.loss == PINN_LOSS_V3_L1SQ)
+    loss += (double)sums[PINN_SUM_ABSF] * (double)sums[PINN_SUM_ABSF] / nf;
+  else
+    loss += (double)sums[PINN_SUM_RES];
+  return loss;
+}
+
+int pinn_loss_grad(pinn_handle_t h, double* loss, float* grad_host) {
+  if (!h) return PINN_E_INVALID;
+  int rc = pinn_loss_grad_device(h);
+  if (rc) return rc;
+  float sums[PINN_NSUMS];
+  CK(cudaMemcpyAsync(sums, h->d_packed + h->net.P + 2, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
+  if (grad_host) {
+    const size_t n = (size_t)h->net.P + (h->cfg.trainable_lambda ? 2 : 0);
+    CK(cudaMemcpyAsync(grad_host, h->d_packed, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (loss) *loss = assemble_loss(h, sums);
+  return PINN_OK;
+}
+
+int pinn_loss_value(pinn_handle_t h, double* loss) {
+  if (!h || !loss) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_loss_value: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  rc = residual_pass(h, GEN_MODE_FORWARD, 0);
+  if (rc) return rc;
+  rc = data_term(h, false);
+  if (rc) return rc;
+  float sums[PINN_NSUMS];
+  float dl = 0.f;
+  CK(cudaMemcpyAsync(sums, h->d_packed + h->net.P + 2, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&dl, h->d_data_loss, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  sums[PINN_SUM_DATA] = dl;
+  *loss = assemble_loss(h, sums);
+  return PINN_OK;
+}
+
+int pinn_adam_config(pinn_handle_t h, float lr, float b1, float b2, float eps) {
+  if (!h) return PINN_E_INVALID;
+  h->lr = lr;
+  h->beta1 = b1;
+  h->beta2 = b2;
+  h->eps = eps;
+  return PINN_OK;
+}
+
+int pinn_adam_reset(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t px = (size_t)h->net.P + 2;
+  CK(cudaMemsetAsync(h->adam.m, 0, px * sizeof(float), h->stream));
+  CK(cudaMemsetAsync(h->adam.v, 0, px * sizeof(float), h->stream));
+  const double init[4] = {0.0, 1.0, 1.0, 0.0};
+  CK(cudaMemcpyAsync(h->adam.scal, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_adam_apply(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  const int n = h->net.P + (h->cfg.trainable_lambda ? 2 : 0);
+  CK(pinn_adam_launch(h->d_theta, h->d_packed, h->adam, n, h->lr, h->beta1, h->beta2, h->eps, h->stream));
+  h->launches += 2;
+  h->weights_dirty = true;
+  return PINN_OK;
+}
+
+int pinn_adam_steps(pinn_handle_t h, int64_t n_steps) {
+  if (!h || n_steps < 0) return PINN_E_INVALID;
+  for (int64_t it = 0; it < n_steps; ++it) {
+    int rc = pinn_loss_grad_device(h);
+    if (rc) return rc;
+    rc = pinn_adam_apply(h);
+    if (rc) return rc;
+  }
+  return PINN_OK;
+}
+
+int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float* f_out, int on_device) {
+  if (!h || !X || n <= 0) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  const float* dX = X;
+  float *tX = nullptr, *tu = nullptr, *tf = nullptr;
+  float *du = u_out, *df = f_out;
+  const size_t no = h->net.n_out, nr = h->net.n_res;
+  auto cleanup = [&]() {
+    if (tX) cudaFree(tX);
+    if (tu) cudaFree(tu);
+    if (tf) cudaFree(tf);
+  };
+  if (!on_device) {
+    cudaError_t e = cudaMalloc(&tX, (size_t)n * 2 * sizeof(float));
+    if (e == cudaSuccess && u_out) e = cudaMalloc(&tu, (size_t)n * no * sizeof(float));
+    if (e == cudaSuccess && f_out) e = cudaMalloc(&tf, (size_t)n * nr * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tX, X, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) {
+      cleanup();
+      h->err = std::string("pinn_predict: ") + cudaGetErrorString(e);
+      return PINN_E_CUDA;
+    }
+    dX = tX;
+    du = tu;
+    df = tf;
+  }
+  if (f_out)
+    rc = run_generic(h, h->S_res, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, df, 0, false, h->d_part, nullptr);
+  else
+    rc = run_generic(h, 1, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, nullptr, 0, false, h->d_part_data, nullptr);
+  if (rc == PINN_OK && !on_device) {
+    cudaError_t e = cudaSuccess;
+    if (u_out) e = cudaMemcpyAsync(u_out, tu, (size_t)n * no * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && f_out) e = cudaMemcpyAsync(f_out, tf, (size_t)n * nr * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      h->err = std::string("pinn_predict: ") + cudaGetErrorString(e);
+      rc = PINN_E_CUDA;
+    }
+  }
+  cleanup();
+  return rc;
+}
+
+int pinn_admm_init(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_init: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  rc = ensure_admm(h);
+  if (rc) return rc;
+  const int64_t need = h->n_f * h->net.n_res;
+  CK(pinn_fill_launch(h->d_z, need, 1.0f, h->stream));
+  CK(pinn_fill_launch(h->d_gamma, need, 1.0f, h->stream));
+  h->launches += 2;
+  return residual_pass(h, GEN_MODE_FORWARD, 1);
+}
+
+int pinn_admm_update(pinn_handle_t h, int quirk) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_update: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_weights(h);
+  if (rc) return rc;
+  return residual_pass(h, GEN_MODE_FORWARD, quirk ? 3 : 2);
+}
+
+int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->d_z && h->n_f > 0, PINN_E_STATE, "pinn_admm_get_state: ADMM state not initialised");
+  const size_t bytes = (size_t)h->n_f * h->net.n_res * sizeof(float);
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (z) CK(cudaMemcpyAsync(z, h->d_z, bytes, k, h->stream));
+  if (gamma) CK(cudaMemcpyAsync(gamma, h->d_gamma, bytes, k, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int on_device) {
+  if (!h) return PINN_E_INVALID;
+  REQUIRE(h->n_f > 0, PINN_E_STATE, "pinn_admm_set_state: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_admm(h);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->n_f * h->net.n_res * sizeof(float);
+  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (z) CK(cudaMemcpyAsync(h->d_z, z, bytes, k, h->stream));
+  if (gamma) CK(cudaMemcpyAsync(h->d_gamma, gamma, bytes, k, h->stream));
+  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+}  // extern "C"

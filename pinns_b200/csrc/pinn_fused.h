@@ -1,0 +1,24 @@
+// Fused thread-per-point kernel family (pinn_fused.cu): host-side state and entry points.
+#pragma once
+#include <string>
+#include "pinn_kernels.h"
+
+struct FusedState {
+  bool enabled = false;
+  int hidden = 0;        // hidden width (all hidden layers equal)
+  int n_hidden = 0;      // number of hidden layers
+  int grid = 0;
+  int threads = 0;
+  size_t smem = 0;
+  float* d_stash = nullptr;   // per-thread activation stash (L2 resident)
+  float* d_part = nullptr;    // [grid][rvlen] per-CTA partial packed vectors
+  int rvlen = 0;
+};
+
+// decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates
+int fused_init(FusedState& fs, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
+void fused_destroy(FusedState& fs);
+// residual term on the collocation points: loss sums, gradient (mode TRAIN) -> packed (overwritten)
+int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
+              int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* packed,
+              cudaStream_t stream, std::string& err);

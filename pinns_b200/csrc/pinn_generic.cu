@@ -1,0 +1,456 @@
+// Generic FP32 kernel: any layer widths, Burgers (4 streams) / Euler (3 streams) /
+// data term (1 stream).  One CTA owns a tile of 32 collocation points at a time and
+// walks the network layer by layer; per-layer activations live in a CTA-private
+// scratch slab (L2 resident), GEMM operands are register tiles:
+//   F/B:  thread = (point, 8 outputs)  -> acc[S][8], weights via broadcast LDG.128
+//   G  :  thread = (8x8 tile of W-bar) -> k-rows staged transposed in shared memory
+// This is the correctness path for every configuration and the production path for
+// nets the fused thread-per-point kernel (pinn_fused.cu) does not cover.
+//
+// Math: SURVEY.md appendix A.2/A.3, i.e. the Taylor-forward + single-reverse schedule of
+// neural_net/net_u/net_f (INF-L2:96-120, AB-ADMM:170-180, EUL:176-198) and the loss
+// variants INF-L2:68-69, INF-ADMM:98-100, ID-L2b:57-58, AB-L2:59-60, AB-ADMM:129-130, EUL:128-133.
+#include "pinn_kernels.h"
+
+namespace {
+
+constexpr int T = PINN_TILE;
+constexpr int GEN_THREADS = 256;
+
+template <int S>
+struct Streams {
+  const float* p[S];
+};
+
+// input streams of weight layer l: the Taylor seeds for l == 0, else the previous hidden block
+template <int S>
+__device__ __forceinline__ Streams<S> layer_inputs(const GenParams& g, float* scr, int l) {
+  Streams<S> r;
+  if (l == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) r.p[s] = scr + g.sd.in0 + s * 8 * T;
+  } else {
+    const int npw = g.net.np[l];
+    float* blk = scr + g.sd.hid[l - 1];
+    r.p[0] = blk;  // a
+#pragma unroll
+    for (int s = 1; s < S; ++s) r.p[s] = blk + (S - 1 + s) * npw * T;  // H_x, H_t, H_xx
+  }
+  return r;
+}
+
+// acc[s][jj] = sum_i in_s[i][lane] * W[i][8*jg + jj]
+template <int S>
+__device__ __forceinline__ void gemm_rows(const Streams<S>& in, int n_in, const float* __restrict__ W, int ldw,
+                                          int jg, int lane, float (&acc)[S][8]) {
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[s][jj] = 0.f;
+  const float* wrow = W + jg * 8;
+#pragma unroll 2
+  for (int i = 0; i < n_in; ++i) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw + 4));
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const float x = in.p[s][i * T + lane];
+      acc[s][0] = fmaf(x, w0.x, acc[s][0]);
+      acc[s][1] = fmaf(x, w0.y, acc[s][1]);
+      acc[s][2] = fmaf(x, w0.z, acc[s][2]);
+      acc[s][3] = fmaf(x, w0.w, acc[s][3]);
+      acc[s][4] = fmaf(x, w1.x, acc[s][4]);
+      acc[s][5] = fmaf(x, w1.y, acc[s][5]);
+      acc[s][6] = fmaf(x, w1.z, acc[s][6]);
+      acc[s][7] = fmaf(x, w1.w, acc[s][7]);
+    }
+  }
+}
+
+// W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
+template <int S>
+__device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const float* zb, int l, float* gp, float* smem) {
+  const int n_in = g.net.n[l], n_out = g.net.n[l + 1];
+  const int np_in = g.net.np[l], np_out = g.net.np[l + 1];
+  const int ldh = np_in + 4, ldz = np_out + 4;
+  float* Hs = smem;
+  float* Zs = smem + T * ldh;
+  const int nti = np_in / 8, ntj = np_out / 8;
+  float* gW = gp + g.net.w_off[l];
+  float* gb = gp + g.net.b_off[l];
+  for (int s = 0; s < S; ++s) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < np_in * T; idx += blockDim.x) {
+      const int i = idx / T, p = idx % T;
+      Hs[p * ldh + i] = (i < n_in) ? hin.p[s][i * T + p] : 0.f;
+    }
+    const float* zsrc = zb + (size_t)s * g.net.npmax * T;
+    for (int idx = threadIdx.x; idx < np_out * T; idx += blockDim.x) {
+      const int j = idx / T, p = idx % T;
+      Zs[p * ldz + j] = (j < n_out) ? zsrc[j * T + p] : 0.f;
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < nti * ntj; task += blockDim.x) {
+      const int ig = task / ntj, jg = task % ntj;
+      float acc[8][8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+      for (int p = 0; p < T; ++p) {
+        const float4 h0 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8 + 4);
+        const float4 z0 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8);
+        const float4 z1 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8 + 4);
+        const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(h[a], z[b], acc[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int i = ig * 8 + a;
+        if (i < n_in) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const int j = jg * 8 + b;
+            if (j < n_out) gW[(size_t)i * n_out + j] += acc[a][b];
+          }
+        }
+      }
+    }
+    if (s == 0) {
+      for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < T; ++p) sum += Zs[p * ldz + j];
+        gb[j] += sum;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct PointSums {
+  float v[PINN_NSUMS];
+  float dl1, dl2;
+};
+
+// residual adjoint f_bar and loss bookkeeping for one residual value (appendix A.3)
+__device__ __forceinline__ float seed_one(const GenParams& g, float f, float cB, bool valid, int64_t idx, PointSums& ps) {
+  const LossCoef& lc = g.lc;
+  float fbar = lc.cA * f;
+  float zz = 0.f, gg = 0.f;
+  const bool admm = (lc.loss == PINN_LOSS_V2_INF_ADMM || lc.loss == PINN_LOSS_V5_ADMM);
+  if (admm && valid) {
+    zz = g.z[idx];
+    gg = g.gamma[idx];
+  }
+  const float sg = (f > 0.f) ? 1.f : ((f < 0.f) ? -1.f : 0.f);
+  fbar += cB * sg + lc.cC * (f - zz) + lc.cD * gg;
+  if (valid) {
+    ps.v[PINN_SUM_F2] += f * f;
+    ps.v[PINN_SUM_ABSF] += fabsf(f);
+    if (admm) {
+      const float t = f - zz + gg / lc.rho;
+      float c = 0.5f * lc.rho * t * t;
+      if (lc.loss == PINN_LOSS_V2_INF_ADMM) c += gg * f;
+      ps.v[PINN_SUM_RES] += c;
+      ps.v[PINN_SUM_MISFIT] += fabsf(f - zz);
+    } else if (lc.loss == PINN_LOSS_V1_INF_L2 || lc.loss == PINN_LOSS_V4_MSE) {
+      ps.v[PINN_SUM_RES] += f * f * lc.inv_nf;
+    }
+  } else {
+    fbar = 0.f;
+  }
+  return fbar;
+}
+
+// soft threshold + dual update (AB-ADMM:185-198,:132; INF-ADMM:205-215,:106-107; EUL:203-215,:137-139)
+__device__ __forceinline__ void admm_one(const GenParams& g, float f, int64_t idx) {
+  if (g.admm_op == 1) {  // z <- f(theta0)  (AB-ADMM:96-97)
+    g.z[idx] = f;
+    return;
+  }
+  const float rho = g.lc.rho;
+  const float kappa = 1.0f / (rho * (float)g.nf_global);
+  float zz = g.z[idx], gg = g.gamma[idx];
+  if (g.admm_op == 3) gg = gg + rho * (f - zz);  // INF-ADMM quirk: the dual advances inside z_update
+  const float val = f + gg / rho;
+  const float c1 = (val > kappa) ? 1.f : 0.f;
+  const float c3 = (val < -1.0f * kappa) ? 1.f : 0.f;
+  const float znew = c1 * (val - kappa) + c3 * (val + kappa);
+  g.z[idx] = znew;
+  g.gamma[idx] = gg + rho * (f - znew);
+}
+
+template <int S>
+__global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenParams g) {
+  extern __shared__ float smem[];
+  const NetDesc& net = g.net;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* scr = g.scratch + (size_t)blockIdx.x * g.sd.total;
+  float* gp = g.part + (size_t)blockIdx.x * g.rvlen;
+  const bool backward = (g.mode != GEN_MODE_FORWARD);
+  const int L = net.L;
+
+  for (int k = threadIdx.x; k < g.rvlen; k += blockDim.x) gp[k] = 0.f;
+  float cB = g.lc.cB;
+  if (g.lc.loss == PINN_LOSS_V3_L1SQ && g.l1_sum != nullptr) cB = 2.0f * g.lc.inv_nf * g.l1_sum[0];
+  const float lam1 = g.theta[net.P], lam2 = g.theta[net.P + 1];
+  PointSums ps;
+#pragma unroll
+  for (int k = 0; k < PINN_NSUMS; ++k) ps.v[k] = 0.f;
+  ps.dl1 = ps.dl2 = 0.f;
+  __syncthreads();
+
+  const int64_t ntiles = (g.N + T - 1) / T;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t pidx = tile * T + lane;
+    const bool valid = pidx < g.N;
+    // ---- Taylor seeds of the input layer (appendix A.2): H0 = 2(X-lb)/(ub-lb)-1 ----
+    if (warp == 0) {
+      float x = net.lbx, t = net.lbt;
+      if (valid) {
+        const float2 xt = *reinterpret_cast<const float2*>(g.X + 2 * pidx);
+        x = xt.x;
+        t = xt.y;
+      }
+      float* in0 = scr + g.sd.in0;
+      in0[0 * T + lane] = 2.0f * (x - net.lbx) / net.spanx - 1.0f;
+      in0[1 * T + lane] = 2.0f * (t - net.lbt) / net.spant - 1.0f;
+      if (S >= 3) {
+        in0[(1 * 8 + 0) * T + lane] = 2.0f / net.spanx;
+        in0[(1 * 8 + 1) * T + lane] = 0.f;
+        in0[(2 * 8 + 0) * T + lane] = 0.f;
+        in0[(2 * 8 + 1) * T + lane] = 2.0f / net.spant;
+      }
+      if (S == 4) {
+        in0[(3 * 8 + 0) * T + lane] = 0.f;
+        in0[(3 * 8 + 1) * T + lane] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ---- forward ----
+    for (int l = 0; l < L; ++l) {
+      const Streams<S> in = layer_inputs<S>(g, scr, l);
+      const int n_in = net.n[l], np_out = net.np[l + 1], n_out = net.n[l + 1];
+      const float* W = g.wp + net.wp_off[l];
+      const float* b = g.theta + net.b_off[l];
+      const bool head = (l == L - 1);
+      for (int jg = warp; jg < np_out / 8; jg += nwarps) {
+        float acc[S][8];
+        gemm_rows<S>(in, n_in, W, np_out, jg, lane, acc);
+        if (!head) {
+          float* blk = scr + g.sd.hid[l];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = jg * 8 + jj;
+            const float z = acc[0][jj] + (j < n_out ? b[j] : 0.f);
+            const float a = pinn_tanh(z);
+            const float d1 = fmaf(-a, a, 1.0f);
+            blk[j * T + lane] = a;
+            if (S >= 3) {
+              const float zx = acc[1][jj], zt = acc[2][jj];
+              blk[(1 * np_out + j) * T + lane] = zx;
+              blk[(2 * np_out + j) * T + lane] = zt;
+              blk[((S - 1 + 1) * np_out + j) * T + lane] = d1 * zx;
+              blk[((S - 1 + 2) * np_out + j) * T + lane] = d1 * zt;
+              if (S == 4) {
+                const float zxx = acc[3][jj];
+                blk[(3 * np_out + j) * T + lane] = zxx;
+                blk[((S - 1 + 3) * np_out + j) * T + lane] = d1 * fmaf(-2.0f * a, zx * zx, zxx);
+              }
+            }
+          }
+        } else {
+          float* Y = scr + g.sd.Y;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const int j = jg * 8 + jj;  // jg == 0: n_out <= 8
+            Y[j * T + lane] = acc[0][jj] + (j < n_out ? b[j] : 0.f);
+#pragma unroll
+            for (int s = 1; s < S; ++s) Y[(s * 8 + j) * T + lane] = acc[s][jj];
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- residual, loss terms, ADMM, adjoint seeds of the head outputs ----
+    int cur = 0;
+    if (warp == 0) {
+      const float* Y = scr + g.sd.Y;
+      float* zb = scr + g.sd.zb[0];
+      const int ldz = net.npmax * T;
+      if (S == 1) {  // data term: adjoints supplied by the caller (appendix A.3, dL/du^)
+        for (int o = 0; o < 8; ++o) {
+          float sd = 0.f;
+          if (o < net.n_out && valid) {
+            if (g.u_out) g.u_out[pidx * net.n_out + o] = Y[o * T + lane];
+            if (g.seed) sd = g.seed[pidx * net.n_out + o];
+          }
+          zb[o * T + lane] = sd;
+        }
+      } else if (net.pde == PINN_PDE_BURGERS) {
+        const float u = Y[lane], ux = Y[(1 * 8) * T + lane], ut = Y[(2 * 8) * T + lane];
+        const float uxx = (S == 4) ? Y[(3 * 8) * T + lane] : 0.f;
+        const float f = ut + lam1 * u * ux - lam2 * uxx;  // INF-L2:118 / AB-ADMM:178
+        if (valid) {
+          if (g.u_out) g.u_out[pidx] = u;
+          if (g.f_out) g.f_out[pidx] = f;
+        }
+        const float fbar = seed_one(g, f, cB, valid, pidx, ps);
+        if (valid && g.admm_op) admm_one(g, f, pidx);
+        ps.dl1 += fbar * u * ux;
+        ps.dl2 -= fbar * uxx;
+        for (int o = 0; o < 8; ++o) {
+          const bool o0 = (o == 0);
+          zb[0 * ldz + o * T + lane] = o0 ? fbar * lam1 * ux : 0.f;
+          zb[1 * ldz + o * T + lane] = o0 ? fbar * lam1 * u : 0.f;
+          zb[2 * ldz + o * T + lane] = o0 ? fbar : 0.f;
+          if (S == 4) zb[3 * ldz + o * T + lane] = o0 ? -lam2 * fbar : 0.f;
+        }
+      } else {  // Euler, outputs (rho,u,E), EUL:176-198 by the product rule
+        const float k = 0.4f;
+        const float r = Y[0 * T + lane], u = Y[1 * T + lane], E = Y[2 * T + lane];
+        const float rx = Y[(8 + 0) * T + lane], ux = Y[(8 + 1) * T + lane], Ex = Y[(8 + 2) * T + lane];
+        const float rt = Y[(16 + 0) * T + lane], ut = Y[(16 + 1) * T + lane], Et = Y[(16 + 2) * T + lane];
+        const float p = k * (E - 0.5f * r * u * u);
+        const float px = k * (Ex - 0.5f * rx * u * u - r * u * ux);
+        const float f1 = rt + rx * u + r * ux;
+        const float f2 = rt * u + r * ut + rx * u * u + 2.0f * r * u * ux + px;
+        const float f3 = Et + ux * E + u * Ex + ux * p + u * px;
+        if (valid) {
+          if (g.u_out) {
+            g.u_out[pidx * 3 + 0] = r;
+            g.u_out[pidx * 3 + 1] = u;
+            g.u_out[pidx * 3 + 2] = E;
+          }
+          if (g.f_out) {
+            g.f_out[pidx * 3 + 0] = f1;
+            g.f_out[pidx * 3 + 1] = f2;
+            g.f_out[pidx * 3 + 2] = f3;
+          }
+        }
+        const float b1 = seed_one(g, f1, cB, valid, pidx * 3 + 0, ps);
+        const float b2 = seed_one(g, f2, cB, valid, pidx * 3 + 1, ps);
+        const float b3 = seed_one(g, f3, cB, valid, pidx * 3 + 2, ps);
+        if (valid && g.admm_op) {
+          admm_one(g, f1, pidx * 3 + 0);
+          admm_one(g, f2, pidx * 3 + 1);
+          admm_one(g, f3, pidx * 3 + 2);
+        }
+        const float p_r = -0.5f * k * u * u, p_u = -k * r * u, p_E = k;
+        const float px_r = -k * u * ux, px_u = -k * (rx * u + r * ux);
+        const float px_rx = -0.5f * k * u * u, px_ux = -k * r * u, px_Ex = k;
+        float yb[3][3];
+        yb[0][0] = b1 * ux + b2 * (ut + 2.0f * u * ux + px_r) + b3 * (ux * p_r + u * px_r);
+        yb[0][1] = b1 * rx + b2 * (rt + 2.0f * rx * u + 2.0f * r * ux + px_u) + b3 * (Ex + ux * p_u + px + u * px_u);
+        yb[0][2] = b3 * (ux + ux * p_E);
+        yb[1][0] = b1 * u + b2 * (u * u + px_rx) + b3 * u * px_rx;
+        yb[1][1] = b1 * r + b2 * (2.0f * r * u + px_ux) + b3 * (E + p + u * px_ux);
+        yb[1][2] = b2 * px_Ex + b3 * (u + u * px_Ex);
+        yb[2][0] = b1 + b2 * u;
+        yb[2][1] = b2 * r;
+        yb[2][2] = b3;
+        for (int s = 0; s < 3; ++s)
+          for (int o = 0; o < 8; ++o) zb[s * ldz + o * T + lane] = (o < 3) ? yb[s][o] : 0.f;
+      }
+    }
+    __syncthreads();
+    if (!backward) continue;
+
+    // ---- reverse sweep ----
+    for (int l = L - 1; l >= 0; --l) {
+      const float* zb = scr + g.sd.zb[cur];
+      const Streams<S> hin = layer_inputs<S>(g, scr, l);
+      weight_grad<S>(g, hin, zb, l, gp, smem);
+      if (l > 0) {
+        Streams<S> zin;
+#pragma unroll
+        for (int s = 0; s < S; ++s) zin.p[s] = zb + (size_t)s * net.npmax * T;
+        const int n_j = net.n[l + 1], np_i = net.np[l];
+        const float* WT = g.wt + net.wt_off[l];
+        const float* blk = scr + g.sd.hid[l - 1];
+        float* zn = scr + g.sd.zb[cur ^ 1];
+        const int ldz = net.npmax * T;
+        for (int ig = warp; ig < np_i / 8; ig += nwarps) {
+          float acc[S][8];
+          gemm_rows<S>(zin, n_j, WT, np_i, ig, lane, acc);
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const int i = ig * 8 + ii;
+            const float a = blk[i * T + lane];
+            const float d1 = fmaf(-a, a, 1.0f);
+            const float hb = acc[0][ii];
+            if (S == 1) {
+              zn[i * T + lane] = d1 * hb;
+            } else {
+              const float d2 = -2.0f * a * d1;
+              const float zx = blk[(1 * np_i + i) * T + lane], zt = blk[(2 * np_i + i) * T + lane];
+              const float hxb = acc[1][ii], htb = acc[2][ii];
+              float zbar = d1 * hb + d2 * (zx * hxb + zt * htb);
+              float zxbar = d1 * hxb;
+              const float ztbar = d1 * htb;
+              if (S == 4) {
+                const float zxx = blk[(3 * np_i + i) * T + lane];
+                const float hxxb = acc[3][ii];
+                const float d3 = -2.0f * d1 * fmaf(-3.0f * a, a, 1.0f);
+                zbar += d2 * zxx * hxxb + d3 * zx * zx * hxxb;
+                zxbar += 2.0f * d2 * zx * hxxb;
+                zn[3 * ldz + i * T + lane] = d1 * hxxb;
+              }
+              zn[0 * ldz + i * T + lane] = zbar;
+              zn[1 * ldz + i * T + lane] = zxbar;
+              zn[2 * ldz + i * T + lane] = ztbar;
+            }
+          }
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+    }
+    cur = 0;
+  }
+
+  // ---- per-CTA partial sums ----
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < PINN_NSUMS; ++k) {
+      const float v = warp_sum(ps.v[k]);
+      if (lane == 0) gp[net.P + 2 + k] += v;
+    }
+    const float d1 = warp_sum(ps.dl1), d2 = warp_sum(ps.dl2);
+    if (lane == 0) {
+      gp[net.P] += d1;
+      gp[net.P + 1] += d2;
+    }
+  }
+}
+
+}  // namespace
+
+size_t pinn_generic_smem_bytes(const NetDesc& net) { return (size_t)T * (2 * net.npmax + 8) * sizeof(float); }
+
+cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream) {
+  const size_t smem = pinn_generic_smem_bytes(g.net);
+  cudaError_t e;
+#define LAUNCH(SS)                                                                                              \
+  e = cudaFuncSetAttribute(pinn_generic_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+  if (e != cudaSuccess) return e;                                                                               \
+  pinn_generic_kernel<SS><<<grid, GEN_THREADS, smem, stream>>>(g);
+  if (S == 1) {
+    LAUNCH(1)
+  } else if (S == 3) {
+    LAUNCH(3)
+  } else {
+    LAUNCH(4)
+  }
+#undef LAUNCH
+  return cudaGetLastError();
+}

@@ -1,6 +1,8 @@
 """GPU parity: CUDA loss / residuals / gradient vs the fp64 oracle on identical
 weights and inputs, through the C ABI.  Tolerance (BASELINE.json north_star, fp32
 path): 1e-5 relative."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -30,7 +32,7 @@ CASES = [
 @pytest.mark.parametrize("name,pde,layers,loss,n_u,n_f", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("path", ["generic", "auto"])
 def test_loss_grad_parity(name, pde, layers, loss, n_u, n_f, path):
-    case = make_case(pde, layers, loss, n_u, n_f, seed=hash(name) % 1000)
+    case = make_case(pde, layers, loss, n_u, n_f, seed=zlib.crc32(name.encode()) % 1000)
     ref = tg.evaluate(case["theta"], case["prob"], case["X_u"], case["u"], case["X_f"], case["z"], case["gamma"])
     eng = make_engine(case, path=path, trainable_lambda=(pde == tg.PDE_BURGERS))
     loss_gpu, grad_gpu = eng.loss_grad()

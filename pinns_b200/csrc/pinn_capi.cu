@@ -525,7 +525,8 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
     int rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
                        h->nf_global > 0 ? h->nf_global : h->n_f, mode,
                        (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
-                       state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, h->d_packed, h->stream, h->err);
+                       state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, h->d_packed, h->stream,
+                       h->err);
     if (rc) return rc;
     h->launches += 2;
     return PINN_OK;

@@ -20,5 +20,5 @@ int fused_init(FusedState& fs, const NetDesc& net, const pinn_config_t& cfg, int
 void fused_destroy(FusedState& fs);
 // residual term on the collocation points: loss sums, gradient (mode TRAIN) -> packed (overwritten)
 int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
-              int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* packed,
-              cudaStream_t stream, std::string& err);
+              int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
+              float* f_out, float* packed, cudaStream_t stream, std::string& err);

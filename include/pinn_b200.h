@@ -148,6 +148,14 @@ int pinn_admm_update(pinn_handle_t h, int inf_admm_quirk); /* z_update then gamm
 int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device); /* [N_f, n_res] each */
 int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int on_device);
 
+/* ---- measurement hooks (bench.py; no reference counterpart) ----
+ * pinn_kernel_timing(1) brackets every launch of the dominant residual(+grad) kernel with CUDA
+ * events on the handle's stream; pinn_kernel_time synchronizes and returns their summed duration.
+ * pinn_measure_fma_peak runs an FFMA-only micro-kernel: the measured FP32 roofline denominator. */
+int pinn_kernel_timing(pinn_handle_t h, int enable);
+int pinn_kernel_time(pinn_handle_t h, double* total_ms, int64_t* n_launches);
+int pinn_measure_fma_peak(int device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,9 @@ PROTOTYPES = {
     "pinn_admm_update": (C.c_int, [_H, C.c_int]),
     "pinn_admm_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_admm_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
+    "pinn_kernel_timing": (C.c_int, [_H, C.c_int]),
+    "pinn_kernel_time": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "pinn_measure_fma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
 

@@ -113,7 +113,55 @@ __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// FFMA-only micro-kernel: 16 independent chains per thread, operands in registers
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = (float)(threadIdx.x + k);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = fmaf(acc[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += acc[k];
+  if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace
+
+cudaError_t pinn_fma_peak(double* tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 4);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 4096, grid = sms * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    fma_peak_kernel<<<grid, threads>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * (double)grid * threads * (double)iters * 8 * 16;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return e;
+}
 
 cudaError_t pinn_repack_launch(const NetDesc& net, const float* theta, float* wp, float* wt, cudaStream_t stream) {
   dim3 grid(32, net.L);

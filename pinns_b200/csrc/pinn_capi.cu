@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "pinn_kernels.h"
 #include "pinn_fused.h"
@@ -55,6 +56,10 @@ struct pinn_handle_s {
   bool l1_ready = false;
 
   FusedState fused;
+
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // pairs (before, after) of the dominant kernel
+  size_t ev_used = 0;
 };
 
 static std::string g_create_err;
@@ -330,6 +335,7 @@ int pinn_destroy(pinn_handle_t h) {
   if (!h) return PINN_OK;
   cudaSetDevice(h->cfg.device);
   fused_destroy(h->fused);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
                    h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
                    h->d_l1sum, h->d_data_loss};
@@ -515,27 +521,44 @@ static int data_term(pinn_handle_t h, bool want_grad) {
   return PINN_OK;
 }
 
+static int timing_mark(pinn_handle_t h) {
+  if (!h->timing) return PINN_OK;
+  if (h->ev_used == h->ev.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  CK(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+  return PINN_OK;
+}
+
 static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
   const bool state = loss_uses_state(h->cfg.loss) || admm_op != 0;
   if (state) {
     int rc = ensure_admm(h);
     if (rc) return rc;
   }
-  if (h->fused.enabled) {
-    int rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
-                       h->nf_global > 0 ? h->nf_global : h->n_f, mode,
-                       (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
-                       state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, h->d_packed, h->stream,
-                       h->err);
-    if (rc) return rc;
-    h->launches += 2;
-    return PINN_OK;
-  }
   int grid = 0;
-  int rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state,
-                       h->d_part, &grid);
+  int rc = timing_mark(h);
   if (rc) return rc;
-  CK(pinn_finalize_launch(h->d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
+  const float* part = h->d_part;
+  if (h->fused.enabled) {
+    rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
+                   h->nf_global > 0 ? h->nf_global : h->n_f, mode,
+                   (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
+                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, &grid, h->stream,
+                   h->err);
+    if (rc) return rc;
+    h->launches += 1;
+    part = h->fused.d_part;
+  } else {
+    rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state,
+                     h->d_part, &grid);
+    if (rc) return rc;
+  }
+  rc = timing_mark(h);
+  if (rc) return rc;
+  CK(pinn_finalize_launch(part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
   h->launches += 1;
   return PINN_OK;
 }
@@ -757,6 +780,34 @@ int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int
   if (gamma) CK(cudaMemcpyAsync(h->d_gamma, gamma, bytes, k, h->stream));
   if (!on_device) CK(cudaStreamSynchronize(h->stream));
   return PINN_OK;
+}
+
+int pinn_kernel_timing(pinn_handle_t h, int enable) {
+  if (!h) return PINN_E_INVALID;
+  h->timing = enable != 0;
+  h->ev_used = 0;
+  return PINN_OK;
+}
+
+int pinn_kernel_time(pinn_handle_t h, double* total_ms, int64_t* n_launches) {
+  if (!h || !total_ms) return PINN_E_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  double tot = 0.0;
+  for (size_t k = 0; k + 1 < h->ev_used; k += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  if (n_launches) *n_launches = (int64_t)(h->ev_used / 2);
+  h->ev_used = 0;
+  return PINN_OK;
+}
+
+int pinn_measure_fma_peak(int device, double* tflops) {
+  if (!tflops) return PINN_E_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return PINN_E_CUDA;
+  return pinn_fma_peak(tflops) == cudaSuccess ? PINN_OK : PINN_E_CUDA;
 }
 
 }  // extern "C"

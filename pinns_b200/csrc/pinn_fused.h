@@ -18,7 +18,7 @@ struct FusedState {
 // decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates
 int fused_init(FusedState& fs, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
 void fused_destroy(FusedState& fs);
-// residual term on the collocation points: loss sums, gradient (mode TRAIN) -> packed (overwritten)
+// residual term on the collocation points: loss sums, gradient (mode TRAIN) -> fs.d_part rows [0, *grid_out)
 int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
-              float* f_out, float* packed, cudaStream_t stream, std::string& err);
+              float* f_out, int* grid_out, cudaStream_t stream, std::string& err);

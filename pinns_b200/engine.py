@@ -61,6 +61,7 @@ class Engine:
         self.n_out = self.layers[-1]
         self.n_res = 1 if pde == "burgers" else 3
         self.trainable_lambda = bool(trainable_lambda)
+        self.loss_kind = loss
         self._h = C.c_void_p()
         capi.check(capi.lib.pinn_create(C.byref(cfg), C.byref(self._h)), None, "pinn_create")
         n = C.c_int64()
@@ -245,6 +246,22 @@ class Engine:
         self._ck(capi.lib.pinn_predict(self._h, Xs.ctypes.data_as(C.c_void_p), n, u.ctypes.data_as(C.c_void_p),
                                        f.ctypes.data_as(C.c_void_p) if want_f else None, 0), "pinn_predict")
         return u, f
+
+    # ---- measurement hooks ----
+    def kernel_timing(self, enable: bool):
+        self._ck(capi.lib.pinn_kernel_timing(self._h, int(enable)), "pinn_kernel_timing")
+
+    def kernel_time(self):
+        """(summed ms, launches) of the dominant residual kernel since kernel_timing(True)."""
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(capi.lib.pinn_kernel_time(self._h, C.byref(ms), C.byref(n)), "pinn_kernel_time")
+        return float(ms.value), int(n.value)
+
+    @staticmethod
+    def measure_fma_peak(device: int = 0) -> float:
+        tf = C.c_double()
+        capi.check(capi.lib.pinn_measure_fma_peak(int(device), C.byref(tf)), None, "pinn_measure_fma_peak")
+        return float(tf.value)
 
     # ---- ADMM ----
     def admm_init(self):

@@ -521,14 +521,15 @@ static int data_term(pinn_handle_t h, bool want_grad) {
   return PINN_OK;
 }
 
-static int timing_mark(pinn_handle_t h) {
+static int timing_event(pinn_handle_t h, cudaEvent_t* out) {
+  *out = nullptr;
   if (!h->timing) return PINN_OK;
   if (h->ev_used == h->ev.size()) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     h->ev.push_back(e);
   }
-  CK(cudaEventRecord(h->ev[h->ev_used++], h->stream));
+  *out = h->ev[h->ev_used++];
   return PINN_OK;
 }
 
@@ -538,27 +539,27 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
     int rc = ensure_admm(h);
     if (rc) return rc;
   }
-  int grid = 0;
-  int rc = timing_mark(h);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = timing_event(h, &e0);
+  if (rc == PINN_OK) rc = timing_event(h, &e1);
   if (rc) return rc;
-  const float* part = h->d_part;
   if (h->fused.enabled) {
     rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
                    h->nf_global > 0 ? h->nf_global : h->n_f, mode,
                    (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
-                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, &grid, h->stream,
-                   h->err);
+                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, h->d_packed, e0, e1,
+                   h->stream, h->err);
     if (rc) return rc;
-    h->launches += 1;
-    part = h->fused.d_part;
-  } else {
-    rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state,
-                     h->d_part, &grid);
-    if (rc) return rc;
+    h->launches += 2;
+    return PINN_OK;
   }
-  rc = timing_mark(h);
+  int grid = 0;
+  if (e0) CK(cudaEventRecord(e0, h->stream));
+  rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state, h->d_part,
+                   &grid);
   if (rc) return rc;
-  CK(pinn_finalize_launch(part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
+  if (e1) CK(cudaEventRecord(e1, h->stream));
+  CK(pinn_finalize_launch(h->d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
   h->launches += 1;
   return PINN_OK;
 }

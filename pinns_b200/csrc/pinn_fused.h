@@ -11,14 +11,17 @@ struct FusedState {
   int threads = 0;
   size_t smem = 0;
   float* d_stash = nullptr;   // per-thread activation stash (L2 resident)
-  float* d_part = nullptr;    // [grid][rvlen] per-CTA partial packed vectors
+  float* d_part = nullptr;    // [grid*warps][region] warp-private gradient / loss accumulators
   int rvlen = 0;
+  int region = 0;            // floats per warp-private accumulator region
 };
 
 // decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates
 int fused_init(FusedState& fs, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
 void fused_destroy(FusedState& fs);
-// residual term on the collocation points: loss sums, gradient (mode TRAIN) -> fs.d_part rows [0, *grid_out)
+// residual term on the collocation points: loss sums (+ gradient in mode TRAIN) -> packed (overwritten).
+// ev_before / ev_after (optional) bracket the main kernel only.
 int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
-              float* f_out, int* grid_out, cudaStream_t stream, std::string& err);
+              float* f_out, float* packed, cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream,
+              std::string& err);

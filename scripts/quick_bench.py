@@ -15,8 +15,11 @@ for _ in range(3): eng.loss_grad_device()
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 K=10
+eng.kernel_timing(True)
 ev[0].record()
 for _ in range(K): eng.loss_grad_device()
 ev[1].record(); torch.cuda.synchronize()
+kms, kn = eng.kernel_time()
 ms = ev[0].elapsed_time(ev[1])/K
+print(f'kernel-only ms={kms/kn:.3f} -> {N/(kms/kn)/1e3:.1f} Mpts/s, frac_of_74.5={N*68320/(kms/kn)/1e9/74.5:.3f}')
 print(f'N={N} ms/step={ms:.3f} Mpts/s={N/ms/1e3:.1f} TFLOPs={N*68320/ms/1e9:.2f} frac_of_74.5={N*68320/ms/1e9/74.5:.3f}')

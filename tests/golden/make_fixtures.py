@@ -1,0 +1,92 @@
+"""Regenerates everything under tests/golden/ (run in the build container, where /root/reference exists):
+
+  data/*.npz          the reference's .mat solution fixtures (x, t, usol [, rhosol, Enersol]) re-saved as
+                      compressed npz -- they are read-only INPUTS of the path, needed on
+                      the GPU box where /root/reference does not exist
+  vectors_*.npz       fp64 oracle outputs (loss, residuals, gradient, dlambda, 5-step TF-1 Adam trajectory) for
+                      seeded inputs, one file per PDE x loss variant x width: they pin the oracle against silent
+                      regressions and give the parity tests reference values that do not depend on torch
+  e2e_*.json          oracle-trained final relative L2 errors for small end-to-end schedules
+
+PARITY UNPINNED by the reference itself (it ships no golden vectors); these are produced by oracle/tf_graph.py,
+which is cross-checked against oracle/taylor.py and finite differences in tests/test_oracle.py.
+"""
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import tf_graph as tg  # noqa: E402
+from oracle.optim import TF1Adam  # noqa: E402
+from tests.helpers import make_case  # noqa: E402
+
+REF = "/root/reference"
+MATS = {
+    "burgers_shock": "Burgers/Data/burgers_shock.mat",
+    "Abgrall_burgers_shock": "Burgers/Data/Abgrall_burgers_shock.mat",
+    "TwoSin_burgers_shock": "Burgers/Data/TwoSin_burgers_shock.mat",
+    "Abgrall_eulers": "Eulers/Data/Abgrall_eulers.mat",
+}
+
+VECTOR_CASES = [
+    # name, pde, layers, loss, n_u, n_f
+    ("burgers20_v1", tg.PDE_BURGERS, [2] + [20] * 8 + [1], tg.LOSS_V1, 100, 512),
+    ("burgers20_v2", tg.PDE_BURGERS, [2] + [20] * 8 + [1], tg.LOSS_V2, 100, 512),
+    ("burgers20_v3", tg.PDE_BURGERS, [2] + [20] * 8 + [1], tg.LOSS_V3, 100, 512),
+    ("burgers20_v4", tg.PDE_BURGERS, [2] + [20] * 8 + [1], tg.LOSS_V4, 100, 512),
+    ("burgers20_v5", tg.PDE_BURGERS, [2] + [20] * 8 + [1], tg.LOSS_V5, 100, 512),
+    ("burgers128_v4", tg.PDE_BURGERS, [2] + [128] * 8 + [1], tg.LOSS_V4, 50, 128),
+    ("burgers200_v4", tg.PDE_BURGERS, [2] + [200] * 8 + [1], tg.LOSS_V4, 50, 96),
+    ("euler200_v6", tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_V6, 64, 128),
+    ("euler200_mse", tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_EULER_MSE, 64, 128),
+]
+
+
+def save_data():
+    import scipy.io
+    for name, rel in MATS.items():
+        d = scipy.io.loadmat(os.path.join(REF, rel))
+        keep = {k: np.asarray(v) for k, v in d.items() if not k.startswith("__")}
+        np.savez_compressed(os.path.join(HERE, "data", name + ".npz"), **keep)
+        print("data", name, {k: v.shape for k, v in keep.items()})
+
+
+def case_seed(name):
+    return zlib.crc32(name.encode()) % 100000
+
+
+def save_vectors():
+    for name, pde, layers, loss, n_u, n_f in VECTOR_CASES:
+        case = make_case(pde, layers, loss, n_u, n_f, seed=case_seed(name))
+        ev = tg.evaluate(case["theta"], case["prob"], case["X_u"], case["u"], case["X_f"], case["z"], case["gamma"])
+        # 5 TF-1 Adam steps in fp64 (theta round-tripped through float32 like a tf.Variable)
+        theta = case["theta"].astype(np.float64)
+        opt = TF1Adam(theta.size)
+        losses = []
+        for _ in range(5):
+            e = tg.evaluate(theta, case["prob"], case["X_u"], case["u"], case["X_f"], case["z"], case["gamma"])
+            losses.append(e.loss)
+            theta = opt.step(theta, e.grad)
+        big = theta.size > 20000
+        rng = np.random.default_rng(1)
+        idx = np.sort(rng.choice(theta.size, 4096, replace=False)) if big else np.arange(theta.size)
+        np.savez_compressed(
+            os.path.join(HERE, "vectors_%s.npz" % name),
+            seed=case_seed(name), n_u=n_u, n_f=n_f, layers=np.asarray(layers), loss=ev.loss, f=ev.f, u_pred=ev.u_pred,
+            dlam=ev.dlam, grad_idx=idx, grad=ev.grad[idx], grad_norm=np.linalg.norm(ev.grad),
+            adam_losses=np.asarray(losses), adam_theta5=theta[idx], adam_theta5_norm=np.linalg.norm(theta))
+        print("vectors", name, "loss", ev.loss, "|grad|", np.linalg.norm(ev.grad))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["data", "vectors"]
+    if "data" in what:
+        save_data()
+    if "vectors" in what:
+        save_vectors()

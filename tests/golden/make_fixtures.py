@@ -84,9 +84,59 @@ def save_vectors():
         print("vectors", name, "loss", ev.loss, "|grad|", np.linalg.norm(ev.grad))
 
 
+def e2e_schedule(full=False):
+    """End-to-end schedules shared by the oracle (here) and the GPU tests: Burgers inference on burgers_shock, nu = 0.01/pi,
+    MSE loss, TF-1 Adam then L-BFGS-B.  full=False: N_f = 2000+456, 1500 Adam steps, 400 L-BFGS iterations (seconds on a
+    GPU, 2 minutes for the oracle).  full=True: BASELINE config 1 (N_u = 100, N_f = 10 000 + 456), 2000 Adam steps, then
+    L-BFGS-B with the reference's options (AB-ADMM:68-72) capped at 3000 iterations."""
+    from oracle import data as odata
+    sol = dict(np.load(os.path.join(HERE, "data", "burgers_shock.npz")))
+    if full:
+        g = odata.burgers_inference_inputs(sol, N_u=100, N_f=10000, seed=1234)
+        layers = [2] + [20] * 8 + [1]
+        theta0 = tg.xavier_init(layers, np.random.default_rng(1234))
+        prob = tg.Problem(layers, g["lb"], g["ub"], pde=tg.PDE_BURGERS, loss=tg.LOSS_V4, lam1=1.0, lam2=0.01 / np.pi)
+        return g, layers, theta0, prob, dict(adam_steps=2000, lbfgs={'maxiter': 3000, 'maxfun': 50000, 'maxcor': 50, 'maxls': 50,
+                                                                    'ftol': 1.0 * np.finfo(float).eps})
+    g = odata.burgers_inference_inputs(sol, N_u=100, N_f=2000, seed=1234)
+    layers = [2] + [20] * 8 + [1]
+    theta0 = tg.xavier_init(layers, np.random.default_rng(1234))
+    prob = tg.Problem(layers, g["lb"], g["ub"], pde=tg.PDE_BURGERS, loss=tg.LOSS_V4, lam1=1.0, lam2=0.01 / np.pi)
+    return g, layers, theta0, prob, dict(adam_steps=1500, lbfgs={'maxiter': 400, 'maxfun': 600, 'maxcor': 50, 'maxls': 50, 'ftol': 1e-9})
+
+
+def save_e2e(full=False):
+    import torch
+    from oracle.optim import lbfgs_minimize
+    torch.set_num_threads(8)
+    g, layers, theta0, prob, sched = e2e_schedule(full)
+    theta = theta0.astype(np.float64)
+    opt = TF1Adam(theta.size)
+    for it in range(sched["adam_steps"]):
+        ev = tg.evaluate(theta, prob, g["X_u"], g["u"], g["X_f"])
+        theta = opt.step(theta, ev.grad)
+    u_adam, _ = tg.predict(theta, prob, g["X_star"])
+    err_adam = tg.relative_l2(g["u_star"], u_adam)
+    loss_adam = tg.evaluate(theta, prob, g["X_u"], g["u"], g["X_f"], want_grad=False).loss
+
+    def fun(x):
+        e = tg.evaluate(x, prob, g["X_u"], g["u"], g["X_f"])
+        return e.loss, e.grad
+    theta, res = lbfgs_minimize(fun, theta, sched["lbfgs"])
+    u_fin, _ = tg.predict(theta, prob, g["X_star"])
+    out = {"error_u_after_adam": err_adam, "loss_after_adam": loss_adam, "error_u_final": tg.relative_l2(g["u_star"], u_fin),
+           "loss_final": float(res.fun), "lbfgs_nit": int(res.nit), "lbfgs_nfev": int(res.nfev)}
+    json.dump(out, open(os.path.join(HERE, "e2e_burgers_inference%s.json" % ("_full" if full else "")), "w"), indent=1)
+    print("e2e", out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["data", "vectors"]
     if "data" in what:
         save_data()
     if "vectors" in what:
         save_vectors()
+    if "e2e" in what:
+        save_e2e()
+    if "e2e_full" in what:
+        save_e2e(True)

@@ -1,0 +1,85 @@
+"""2-GPU test of the sharded path (skipped with fewer than two GPUs): one process per GPU, NCCL allreduce of the packed
+vector; the combined gradient and the Adam-updated parameters must equal the single-GPU result on the same points."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+B20 = [2] + [20] * 8 + [1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, out):
+    import torch
+    import torch.distributed as dist
+    from pinns_b200 import Engine
+    from pinns_b200.distributed import DataParallelStepper, shard_range
+    from pinns_b200.models import xavier_init_flat
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        eng = Engine(B20, [-1, 0], [1, 0.99], loss="v4", lambda2=0.01 / np.pi, device=rank)
+        eng.use_torch_stream()
+        eng.set_params(xavier_init_flat(B20, np.random.default_rng(3)))
+        rng = np.random.default_rng(4)
+        X_u = np.array([-1, 0]) + np.array([2, 0.99]) * rng.random((50, 2))
+        eng.set_data(X_u, np.sin(X_u[:, 0:1]))
+        first, cnt = shard_range(n_total, rank, world)
+        eng.sample_collocation(1234, first, cnt, n_total)
+        st = DataParallelStepper(eng, rank, world)
+        st.loss_grad_device()
+        torch.cuda.synchronize()
+        packed = eng.packed_tensor().cpu().numpy().copy()
+        st.adam_step()
+        theta = eng.get_params()
+        if rank == 0:
+            out.put((packed, theta))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_gradient_equals_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pinns_b200 import Engine
+    from pinns_b200.models import xavier_init_flat
+    n_total = 200001
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    packed2, theta2 = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    eng = Engine(B20, [-1, 0], [1, 0.99], loss="v4", lambda2=0.01 / np.pi, device=0)
+    eng.set_params(xavier_init_flat(B20, np.random.default_rng(3)))
+    rng = np.random.default_rng(4)
+    X_u = np.array([-1, 0]) + np.array([2, 0.99]) * rng.random((50, 2))
+    eng.set_data(X_u, np.sin(X_u[:, 0:1]))
+    eng.sample_collocation(1234, 0, n_total, n_total)
+    eng.loss_grad_device()
+    eng.synchronize()
+    packed1 = eng.packed_tensor().cpu().numpy().copy()
+    eng.loss_grad_device()
+    eng.adam_apply()
+    theta1 = eng.get_params()
+    P = eng.num_params
+    assert np.linalg.norm(packed2[:P] - packed1[:P]) <= 5e-6 * np.linalg.norm(packed1[:P])
+    assert np.allclose(packed2[P + 2:P + 4], packed1[P + 2:P + 4], rtol=1e-5)
+    assert np.linalg.norm(theta2 - theta1) <= 1e-5 * np.linalg.norm(theta1)

@@ -248,6 +248,12 @@ def run_ours(args, rank, world, local_rank):
     peak_nominal = 148 * 128 * 2 * sm_max * 1e6 / 1e12
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = nf * F_POINT / (k_avg_ms * 1e-3) / 1e12
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel (per point x points per launch)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_fused_traffic.json")))
+        traffic = float(tr["dram_bytes_per_point"]) * nf
+    except Exception:
+        pass
     roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
                 "frac": achieved / peak_meas if peak_meas > 0 else None,
                 "peak_source": "FFMA-only micro-kernel measured on this GPU in this run (of measured); "
@@ -255,7 +261,8 @@ def run_ours(args, rank, world, local_rank):
                 "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
                 "kernel": "pinn_fused_kernel<20,true>", "kernel_ms": k_avg_ms, "kernel_launches": k_n,
                 "kernel_share_of_step": k_avg_ms / ms_step,
-                "flops_per_point": F_POINT, "points_per_launch": nf, "traffic": None,
+                "flops_per_point": F_POINT, "points_per_launch": nf, "traffic": traffic,
+                "traffic_source": "profiles/r01_fused_traffic.json (ncu dram__bytes_read+write per point x points per launch)",
                 "hbm_algorithmic_bytes_per_point": 8}
     cpu = None
     if world == 1 or True:

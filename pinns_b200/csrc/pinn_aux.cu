@@ -69,22 +69,12 @@ __global__ void data_seed_kernel(const float* __restrict__ u_pred, const float* 
   for (int64_t k = threadIdx.x; k < n; k += blockDim.x) seed[k] = scale * (u_data[k] - u_pred[k]);
 }
 
-// tf.train.AdamOptimizer (TF-1 ApplyAdam, appendix A.4): epsilon outside the bias correction
-__global__ void adam_prep_kernel(double* scal, float lr, float beta1, float beta2) {
-  const double t = scal[0] + 1.0;
-  const double b1p = scal[1] * (double)beta1, b2p = scal[2] * (double)beta2;
-  scal[0] = t;
-  scal[1] = b1p;
-  scal[2] = b2p;
-  scal[3] = (double)lr * sqrt(1.0 - b2p) / (1.0 - b1p);
-}
-
+// tf.train.AdamOptimizer (TF-1 ApplyAdam, appendix A.4): epsilon outside the bias correction;
+// alpha = lr*sqrt(1-beta2^t)/(1-beta1^t) is formed on the host (double) from the handle's step count
 __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
-                            float* __restrict__ v, const double* __restrict__ scal, int n, float beta1, float beta2,
-                            float eps) {
+                            float* __restrict__ v, int n, float alpha, float beta1, float beta2, float eps) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const float alpha = (float)scal[3];
   const float g = grad[k];
   float mk = m[k], vk = v[k];
   mk += (g - mk) * (1.0f - beta1);
@@ -181,10 +171,9 @@ cudaError_t pinn_data_seed_launch(const float* u_pred, const float* u_data, int6
   return cudaGetLastError();
 }
 
-cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, int n, float lr, float beta1, float beta2,
+cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, int n, float alpha, float beta1, float beta2,
                              float eps, cudaStream_t stream) {
-  adam_prep_kernel<<<1, 1, 0, stream>>>(st.scal, lr, beta1, beta2);
-  adam_kernel<<<(n + 255) / 256, 256, 0, stream>>>(theta, packed, st.m, st.v, st.scal, n, beta1, beta2, eps);
+  adam_kernel<<<(n + 255) / 256, 256, 0, stream>>>(theta, packed, st.m, st.v, n, alpha, beta1, beta2, eps);
   return cudaGetLastError();
 }
 

@@ -44,8 +44,10 @@ struct pinn_handle_s {
   float* d_gamma = nullptr;
   int64_t admm_cap = 0;
 
-  AdamState adam = {nullptr, nullptr, nullptr};
+  AdamState adam = {nullptr, nullptr};
   float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+  int64_t adam_t = 0;               // steps applied so far (TF's beta1_power / beta2_power, kept in double on the host)
+  double b1pow = 1.0, b2pow = 1.0;
 
   float* d_scratch = nullptr;
   int gen_grid_max = 0;
@@ -146,6 +148,10 @@ static int gen_grid_for(const pinn_handle_s* h, int64_t n) {
 // one launch of the generic kernel; returns the grid used through *grid_out
 static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
                        float* u_out, float* f_out, int admm_op, bool use_state, float* part, int* grid_out) {
+  {
+    int rcw = ensure_weights(h);  // padded / transposed weight copies are only needed by this kernel
+    if (rcw) return rcw;
+  }
   GenParams g;
   memset(&g, 0, sizeof(g));
   g.net = h->net;
@@ -310,7 +316,6 @@ int pinn_create(const pinn_config_t* cfg, pinn_handle_t* out) {
   if ((e = cudaMemset(h->d_data_loss, 0, sizeof(float))) != cudaSuccess) return fail("cudaMemset", e);
   if ((e = cudaMalloc(&h->adam.m, px * sizeof(float))) != cudaSuccess) return fail("cudaMalloc m", e);
   if ((e = cudaMalloc(&h->adam.v, px * sizeof(float))) != cudaSuccess) return fail("cudaMalloc v", e);
-  if ((e = cudaMalloc(&h->adam.scal, 4 * sizeof(double))) != cudaSuccess) return fail("cudaMalloc adam scal", e);
   *out = h;
   int rc = pinn_adam_reset(h);
   if (rc != PINN_OK) {
@@ -341,7 +346,6 @@ int pinn_destroy(pinn_handle_t h) {
                    h->d_l1sum, h->d_data_loss};
   for (float* b : bufs)
     if (b) cudaFree(b);
-  if (h->adam.scal) cudaFree(h->adam.scal);
   delete h;
   return PINN_OK;
 }
@@ -533,7 +537,19 @@ static int timing_event(pinn_handle_t h, cudaEvent_t* out) {
   return PINN_OK;
 }
 
-static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
+// the squared data term rides inside the fused kernel (extra batches); V1's un-squared norm needs ||r|| first
+static bool fused_handles_data(const pinn_handle_s* h) {
+  return h->fused.enabled && h->cfg.loss != PINN_LOSS_V1_INF_L2 && h->n_u > 0 && h->data_weight != 0.0f;
+}
+
+static float adam_next_alpha(pinn_handle_s* h) {
+  h->adam_t += 1;
+  h->b1pow *= (double)h->beta1;
+  h->b2pow *= (double)h->beta2;
+  return (float)((double)h->lr * std::sqrt(1.0 - h->b2pow) / (1.0 - h->b1pow));
+}
+
+static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam = false) {
   const bool state = loss_uses_state(h->cfg.loss) || admm_op != 0;
   if (state) {
     int rc = ensure_admm(h);
@@ -544,13 +560,27 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op) {
   if (rc == PINN_OK) rc = timing_event(h, &e1);
   if (rc) return rc;
   if (h->fused.enabled) {
+    const bool with_data = fused_handles_data(h);
+    AdamFused ad;
+    if (fuse_adam) {
+      ad.n = h->net.P + (h->cfg.trainable_lambda ? 2 : 0);
+      ad.theta = h->d_theta;
+      ad.m = h->adam.m;
+      ad.v = h->adam.v;
+      ad.alpha = adam_next_alpha(h);
+      ad.beta1 = h->beta1;
+      ad.beta2 = h->beta2;
+      ad.eps = h->eps;
+    }
     rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
                    h->nf_global > 0 ? h->nf_global : h->n_f, mode,
                    (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
-                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, h->d_packed, e0, e1,
-                   h->stream, h->err);
+                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr,
+                   with_data ? h->d_Xu : nullptr, with_data ? h->d_u : nullptr, h->n_u,
+                   with_data ? h->data_weight / (float)h->n_u : 0.f, h->d_packed, ad, e0, e1, h->stream, h->err);
     if (rc) return rc;
     h->launches += 2;
+    if (fuse_adam) h->weights_dirty = true;
     return PINN_OK;
   }
   int grid = 0;
@@ -568,9 +598,7 @@ int pinn_l1_pass1(pinn_handle_t h, float** dev_sum) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_l1_pass1: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
-  rc = residual_pass(h, GEN_MODE_FORWARD, 0);
+  int rc = residual_pass(h, GEN_MODE_FORWARD, 0);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->d_l1sum, h->d_packed + h->net.P + 2 + PINN_SUM_ABSF, sizeof(float), cudaMemcpyDeviceToDevice,
                      h->stream));
@@ -583,8 +611,7 @@ int pinn_loss_grad_device(pinn_handle_t h) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_loss_grad: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
+  int rc = PINN_OK;
   if (h->cfg.loss == PINN_LOSS_V3_L1SQ && !h->l1_ready) {
     rc = pinn_l1_pass1(h, nullptr);
     if (rc) return rc;
@@ -592,6 +619,7 @@ int pinn_loss_grad_device(pinn_handle_t h) {
   rc = residual_pass(h, GEN_MODE_TRAIN, 0);
   if (rc) return rc;
   h->l1_ready = false;
+  if (fused_handles_data(h)) return PINN_OK;
   return data_term(h, true);
 }
 
@@ -630,9 +658,7 @@ int pinn_loss_value(pinn_handle_t h, double* loss) {
   if (!h || !loss) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_loss_value: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
-  rc = residual_pass(h, GEN_MODE_FORWARD, 0);
+  int rc = residual_pass(h, GEN_MODE_FORWARD, 0);
   if (rc) return rc;
   rc = data_term(h, false);
   if (rc) return rc;
@@ -661,9 +687,8 @@ int pinn_adam_reset(pinn_handle_t h) {
   const size_t px = (size_t)h->net.P + 2;
   CK(cudaMemsetAsync(h->adam.m, 0, px * sizeof(float), h->stream));
   CK(cudaMemsetAsync(h->adam.v, 0, px * sizeof(float), h->stream));
-  const double init[4] = {0.0, 1.0, 1.0, 0.0};
-  CK(cudaMemcpyAsync(h->adam.scal, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  h->adam_t = 0;
+  h->b1pow = h->b2pow = 1.0;
   return PINN_OK;
 }
 
@@ -671,16 +696,32 @@ int pinn_adam_apply(pinn_handle_t h) {
   if (!h) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));
   const int n = h->net.P + (h->cfg.trainable_lambda ? 2 : 0);
-  CK(pinn_adam_launch(h->d_theta, h->d_packed, h->adam, n, h->lr, h->beta1, h->beta2, h->eps, h->stream));
-  h->launches += 2;
+  CK(pinn_adam_launch(h->d_theta, h->d_packed, h->adam, n, adam_next_alpha(h), h->beta1, h->beta2, h->eps, h->stream));
+  h->launches += 1;
   h->weights_dirty = true;
   return PINN_OK;
 }
 
 int pinn_adam_steps(pinn_handle_t h, int64_t n_steps) {
   if (!h || n_steps < 0) return PINN_E_INVALID;
+  REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_adam_steps: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
+  // single-GPU fast lane: when the fused kernel also carries the data term, a step is two launches
+  // (residual+grad kernel, finalize+Adam) with no host round trip
+  const bool lane2 = h->fused.enabled && (fused_handles_data(h) || h->n_u == 0 || h->data_weight == 0.0f);
   for (int64_t it = 0; it < n_steps; ++it) {
-    int rc = pinn_loss_grad_device(h);
+    int rc;
+    if (lane2) {
+      if (h->cfg.loss == PINN_LOSS_V3_L1SQ) {
+        rc = pinn_l1_pass1(h, nullptr);
+        if (rc) return rc;
+      }
+      rc = residual_pass(h, GEN_MODE_TRAIN, 0, /*fuse_adam=*/true);
+      h->l1_ready = false;
+      if (rc) return rc;
+      continue;
+    }
+    rc = pinn_loss_grad_device(h);
     if (rc) return rc;
     rc = pinn_adam_apply(h);
     if (rc) return rc;
@@ -691,8 +732,7 @@ int pinn_adam_steps(pinn_handle_t h, int64_t n_steps) {
 int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float* f_out, int on_device) {
   if (!h || !X || n <= 0) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
+  int rc = PINN_OK;
   const float* dX = X;
   float *tX = nullptr, *tu = nullptr, *tf = nullptr;
   float *du = u_out, *df = f_out;
@@ -738,9 +778,7 @@ int pinn_admm_init(pinn_handle_t h) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_init: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
-  rc = ensure_admm(h);
+  int rc = ensure_admm(h);
   if (rc) return rc;
   const int64_t need = h->n_f * h->net.n_res;
   CK(pinn_fill_launch(h->d_z, need, 1.0f, h->stream));
@@ -753,8 +791,7 @@ int pinn_admm_update(pinn_handle_t h, int quirk) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_update: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_weights(h);
-  if (rc) return rc;
+  int rc = PINN_OK;
   return residual_pass(h, GEN_MODE_FORWARD, quirk ? 3 : 2);
 }
 

@@ -3,6 +3,15 @@
 #include <string>
 #include "pinn_kernels.h"
 
+// optional Adam update fused into the finalize kernel (n = 0: off); alpha = lr_t of TF-1 Adam, computed on the host
+struct AdamFused {
+  int n = 0;
+  float* theta = nullptr;
+  float* m = nullptr;
+  float* v = nullptr;
+  float alpha = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+};
+
 struct FusedState {
   bool enabled = false;
   int hidden = 0;        // hidden width (all hidden layers equal)
@@ -19,9 +28,10 @@ struct FusedState {
 // decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates
 int fused_init(FusedState& fs, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
 void fused_destroy(FusedState& fs);
-// residual term on the collocation points: loss sums (+ gradient in mode TRAIN) -> packed (overwritten).
+// residual term on the collocation points (+ the squared data term on Xu/ud as extra batches when Xu != null):
+// loss sums (+ gradient in mode TRAIN) -> packed (overwritten); optional fused Adam update of theta.
 // ev_before / ev_after (optional) bracket the main kernel only.
 int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
-              float* f_out, float* packed, cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream,
-              std::string& err);
+              float* f_out, const float* Xu, const float* ud, int64_t n_u, float data_c, float* packed, const AdamFused& ad,
+              cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream, std::string& err);

@@ -48,9 +48,8 @@ cudaError_t pinn_data_seed_launch(const float* u_pred, const float* u_data, int6
 struct AdamState {
   float* m;
   float* v;
-  double* scal;  // [0] t, [1] beta1^t, [2] beta2^t, [3] lr_t
 };
-cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, int n, float lr, float beta1, float beta2,
+cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, int n, float alpha, float beta1, float beta2,
                              float eps, cudaStream_t stream);
 cudaError_t pinn_sample_launch(float* X, int64_t n, uint64_t seed, uint64_t first_index, float lbx, float lbt, float spanx,
                                float spant, cudaStream_t stream);

@@ -1,0 +1,29 @@
+"""Step time / throughput of the other BASELINE configs (parity-test cases, not bench lines)."""
+import sys, time, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from pinns_b200 import Engine
+from tests.helpers import rand_theta
+
+def run(name, layers, pde, loss, n_u, n_f, steps=20, fpp=None):
+    eng = Engine(layers, [-1, 0], [1, 0.99], pde=pde, loss=loss, lambda2=0.01 / np.pi, rho=40.0)
+    eng.use_torch_stream()
+    eng.set_params(rand_theta(layers, np.random.default_rng(0)))
+    rng = np.random.default_rng(1)
+    eng.set_data(rng.random((n_u, 2)), rng.random((n_u, layers[-1])))
+    eng.sample_collocation(1234, 0, n_f)
+    if loss == 'v5': eng.admm_init()
+    for _ in range(3): eng.adam_steps(1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.adam_steps(steps); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tf = '' if fpp is None else ' %.2f TFLOP/s (%.1f%% of 74.5)' % (n_f * fpp / ms / 1e9, 100 * n_f * fpp / ms / 1e9 / 74.5)
+    print('%-34s path=%-7s N_f=%-9d %9.3f ms/step %10.2f Mpts/s%s' % (name, eng.kernel_path, n_f, ms, n_f / ms / 1e3, tf))
+
+run('config1 burgers20 N=10456', [2] + [20] * 8 + [1], 'burgers', 'v1', 100, 10456, 200, 68320)
+run('burgers20 N=1000 (AB batch)', [2] + [20] * 8 + [1], 'burgers', 'v5', 100, 1000, 200, 68320)
+run('burgers20 N=1M', [2] + [20] * 8 + [1], 'burgers', 'v4', 100, 1 << 20, 20, 68320)
+run('config3 euler200x5 N=1000', [2] + [200] * 5 + [3], 'euler', 'v5', 200, 1000, 50, 2895600)
+run('euler200x5 N=65536', [2] + [200] * 5 + [3], 'euler', 'v5', 200, 65536, 5, 2895600)
+run('config5 burgers128 N=262144', [2] + [128] * 8 + [1], 'burgers', 'v4', 100, 262144, 3, 2759680)
+run('burgers200x8 N=1000 (AB-L2)', [2] + [200] * 8 + [1], 'burgers', 'v4', 100, 1000, 50, 6731200)

@@ -88,7 +88,7 @@ def e2e_schedule(full=False):
     """End-to-end schedules shared by the oracle (here) and the GPU tests: Burgers inference on burgers_shock, nu = 0.01/pi,
     MSE loss, TF-1 Adam then L-BFGS-B.  full=False: N_f = 2000+456, 1500 Adam steps, 400 L-BFGS iterations (seconds on a
     GPU, 2 minutes for the oracle).  full=True: BASELINE config 1 (N_u = 100, N_f = 10 000 + 456), 2000 Adam steps, then
-    L-BFGS-B with the reference's options (AB-ADMM:68-72) capped at 3000 iterations."""
+    L-BFGS-B with the reference's options (AB-L2:68-72: maxiter 50000, ftol = eps), capped at 15000 iterations."""
     from oracle import data as odata
     sol = dict(np.load(os.path.join(HERE, "data", "burgers_shock.npz")))
     if full:
@@ -96,7 +96,7 @@ def e2e_schedule(full=False):
         layers = [2] + [20] * 8 + [1]
         theta0 = tg.xavier_init(layers, np.random.default_rng(1234))
         prob = tg.Problem(layers, g["lb"], g["ub"], pde=tg.PDE_BURGERS, loss=tg.LOSS_V4, lam1=1.0, lam2=0.01 / np.pi)
-        return g, layers, theta0, prob, dict(adam_steps=2000, lbfgs={'maxiter': 3000, 'maxfun': 50000, 'maxcor': 50, 'maxls': 50,
+        return g, layers, theta0, prob, dict(adam_steps=2000, lbfgs={'maxiter': 15000, 'maxfun': 50000, 'maxcor': 50, 'maxls': 50,
                                                                     'ftol': 1.0 * np.finfo(float).eps})
     g = odata.burgers_inference_inputs(sol, N_u=100, N_f=2000, seed=1234)
     layers = [2] + [20] * 8 + [1]
@@ -108,7 +108,7 @@ def e2e_schedule(full=False):
 def save_e2e(full=False):
     import torch
     from oracle.optim import lbfgs_minimize
-    torch.set_num_threads(8)
+    torch.set_num_threads(6)
     g, layers, theta0, prob, sched = e2e_schedule(full)
     theta = theta0.astype(np.float64)
     opt = TF1Adam(theta.size)

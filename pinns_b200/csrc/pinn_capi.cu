@@ -140,9 +140,19 @@ static int ensure_weights(pinn_handle_t h) {
   return PINN_OK;
 }
 
-static int gen_grid_for(const pinn_handle_s* h, int64_t n) {
-  const int64_t tiles = (n + PINN_TILE - 1) / PINN_TILE;
-  return (int)(tiles < h->gen_grid_max ? (tiles > 0 ? tiles : 1) : h->gen_grid_max);
+// grid and cluster size of the generic kernel: with fewer tiles than CTA slots, a cluster of up to 8 CTAs shares a tile
+static int gen_grid_for(const pinn_handle_s* h, int64_t n, int* cluster) {
+  int64_t tiles = (n + PINN_TILE - 1) / PINN_TILE;
+  if (tiles < 1) tiles = 1;
+  int cs = 1;
+  while (cs < 8 && tiles * (cs * 2) <= h->gen_grid_max) cs *= 2;
+  // narrow layers have too few 8-wide output groups to share
+  int groups = 1;
+  for (int l = 1; l <= h->net.L; ++l) groups = h->net.np[l] / 8 > groups ? h->net.np[l] / 8 : groups;
+  while (cs > 1 && cs * 8 > groups * 2) cs /= 2;
+  *cluster = cs;
+  const int64_t clusters = tiles < h->gen_grid_max / cs ? tiles : h->gen_grid_max / cs;
+  return (int)(clusters * cs);
 }
 
 // one launch of the generic kernel; returns the grid used through *grid_out
@@ -174,7 +184,7 @@ static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* 
   g.scratch = h->d_scratch;
   g.part = part;
   g.rvlen = h->rvlen;
-  const int grid = gen_grid_for(h, n);
+  const int grid = gen_grid_for(h, n, &g.cluster);
   CK(pinn_generic_launch(g, S, grid, h->stream));
   h->launches += 1;
   if (grid_out) *grid_out = grid;

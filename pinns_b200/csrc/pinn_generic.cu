@@ -10,12 +10,27 @@
 // Math: SURVEY.md appendix A.2/A.3, i.e. the Taylor-forward + single-reverse schedule of
 // neural_net/net_u/net_f (INF-L2:96-120, AB-ADMM:170-180, EUL:176-198) and the loss
 // variants INF-L2:68-69, INF-ADMM:98-100, ID-L2b:57-58, AB-L2:59-60, AB-ADMM:129-130, EUL:128-133.
+#include <cstring>
+
 #include "pinn_kernels.h"
 
 namespace {
 
 constexpr int T = PINN_TILE;
 constexpr int GEN_THREADS = 256;
+
+// A 32-point tile is owned by a cluster of `cs` CTAs (cs = 1 at large N; up to 8 when the job has fewer tiles than the
+// GPU has CTA slots, e.g. the reference's N_f = 1000 batches of a 200-wide net = 32 tiles): the CTAs split the output
+// neurons of every layer / the tiles of every weight gradient and meet at cluster barriers; activations travel through
+// the tile's global scratch slab (barrier.cluster release/acquire orders the writes and invalidates L1).
+__device__ __forceinline__ void tile_sync(int cs) {
+  if (cs == 1) {
+    __syncthreads();
+  } else {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
+}
 
 template <int S>
 struct Streams {
@@ -69,7 +84,8 @@ __device__ __forceinline__ void gemm_rows(const Streams<S>& in, int n_in, const 
 
 // W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
 template <int S>
-__device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const float* zb, int l, float* gp, float* smem) {
+__device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const float* zb, int l, float* gp, float* smem,
+                            int crank, int cs) {
   const int n_in = g.net.n[l], n_out = g.net.n[l + 1];
   const int np_in = g.net.np[l], np_out = g.net.np[l + 1];
   const int ldh = np_in + 4, ldz = np_out + 4;
@@ -90,7 +106,7 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
       Zs[p * ldz + j] = (j < n_out) ? zsrc[j * T + p] : 0.f;
     }
     __syncthreads();
-    for (int task = threadIdx.x; task < nti * ntj; task += blockDim.x) {
+    for (int task = crank * blockDim.x + threadIdx.x; task < nti * ntj; task += cs * blockDim.x) {
       const int ig = task / ntj, jg = task % ntj;
       float acc[8][8];
 #pragma unroll
@@ -122,7 +138,7 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
         }
       }
     }
-    if (s == 0) {
+    if (s == 0 && crank == 0) {
       for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
         float sum = 0.f;
 #pragma unroll 8
@@ -192,7 +208,9 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
   extern __shared__ float smem[];
   const NetDesc& net = g.net;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* scr = g.scratch + (size_t)blockIdx.x * g.sd.total;
+  const int cs = g.cluster;                       // CTAs per tile
+  const int crank = blockIdx.x % cs, cid = blockIdx.x / cs, nclusters = gridDim.x / cs;
+  float* scr = g.scratch + (size_t)cid * g.sd.total;
   float* gp = g.part + (size_t)blockIdx.x * g.rvlen;
   const bool backward = (g.mode != GEN_MODE_FORWARD);
   const int L = net.L;
@@ -208,11 +226,11 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
   __syncthreads();
 
   const int64_t ntiles = (g.N + T - 1) / T;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = cid; tile < ntiles; tile += nclusters) {
     const int64_t pidx = tile * T + lane;
     const bool valid = pidx < g.N;
     // ---- Taylor seeds of the input layer (appendix A.2): H0 = 2(X-lb)/(ub-lb)-1 ----
-    if (warp == 0) {
+    if (warp == 0 && crank == 0) {
       float x = net.lbx, t = net.lbt;
       if (valid) {
         const float2 xt = *reinterpret_cast<const float2*>(g.X + 2 * pidx);
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
         in0[(3 * 8 + 1) * T + lane] = 0.f;
       }
     }
-    __syncthreads();
+    tile_sync(cs);
 
     // ---- forward ----
     for (int l = 0; l < L; ++l) {
@@ -242,7 +260,7 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
       const float* W = g.wp + net.wp_off[l];
       const float* b = g.theta + net.b_off[l];
       const bool head = (l == L - 1);
-      for (int jg = warp; jg < np_out / 8; jg += nwarps) {
+      for (int jg = crank * nwarps + warp; jg < np_out / 8; jg += cs * nwarps) {
         float acc[S][8];
         gemm_rows<S>(in, n_in, W, np_out, jg, lane, acc);
         if (!head) {
@@ -278,12 +296,12 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
           }
         }
       }
-      __syncthreads();
+      tile_sync(cs);
     }
 
     // ---- residual, loss terms, ADMM, adjoint seeds of the head outputs ----
     int cur = 0;
-    if (warp == 0) {
+    if (warp == 0 && crank == 0) {
       const float* Y = scr + g.sd.Y;
       float* zb = scr + g.sd.zb[0];
       const int ldz = net.npmax * T;
@@ -362,14 +380,14 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
           for (int o = 0; o < 8; ++o) zb[s * ldz + o * T + lane] = (o < 3) ? yb[s][o] : 0.f;
       }
     }
-    __syncthreads();
+    tile_sync(cs);
     if (!backward) continue;
 
     // ---- reverse sweep ----
     for (int l = L - 1; l >= 0; --l) {
       const float* zb = scr + g.sd.zb[cur];
       const Streams<S> hin = layer_inputs<S>(g, scr, l);
-      weight_grad<S>(g, hin, zb, l, gp, smem);
+      weight_grad<S>(g, hin, zb, l, gp, smem, crank, cs);
       if (l > 0) {
         Streams<S> zin;
 #pragma unroll
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
         const float* blk = scr + g.sd.hid[l - 1];
         float* zn = scr + g.sd.zb[cur ^ 1];
         const int ldz = net.npmax * T;
-        for (int ig = warp; ig < np_i / 8; ig += nwarps) {
+        for (int ig = crank * nwarps + warp; ig < np_i / 8; ig += cs * nwarps) {
           float acc[S][8];
           gemm_rows<S>(zin, n_j, WT, np_i, ig, lane, acc);
 #pragma unroll
@@ -411,7 +429,7 @@ __global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenPara
             }
           }
         }
-        __syncthreads();
+        tile_sync(cs);
         cur ^= 1;
       }
     }
@@ -439,11 +457,25 @@ size_t pinn_generic_smem_bytes(const NetDesc& net) { return (size_t)T * (2 * net
 
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream) {
   const size_t smem = pinn_generic_smem_bytes(g.net);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   cudaError_t e;
 #define LAUNCH(SS)                                                                                              \
   e = cudaFuncSetAttribute(pinn_generic_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
   if (e != cudaSuccess) return e;                                                                               \
-  pinn_generic_kernel<SS><<<grid, GEN_THREADS, smem, stream>>>(g);
+  e = cudaLaunchKernelEx(&cfg, pinn_generic_kernel<SS>, g);                                                     \
+  if (e != cudaSuccess) return e;
   if (S == 1) {
     LAUNCH(1)
   } else if (S == 3) {

@@ -34,6 +34,7 @@ struct GenParams {
   float* scratch;
   float* part;          // [grid][rvlen] per-CTA partial packed vectors
   int rvlen;
+  int cluster;          // CTAs per 32-point tile (1, 2, 4 or 8); grid = clusters * cluster
 };
 
 size_t pinn_generic_smem_bytes(const NetDesc& net);

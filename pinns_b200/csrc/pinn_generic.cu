@@ -54,32 +54,49 @@ __device__ __forceinline__ Streams<S> layer_inputs(const GenParams& g, float* sc
   return r;
 }
 
+// packed fp32 FMA (fma.rn.f32x2 -> FFMA2, sm_100+): two IEEE fp32 FMAs per issue slot
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+
 // acc[s][jj] = sum_i in_s[i][lane] * W[i][8*jg + jj]
 template <int S>
 __device__ __forceinline__ void gemm_rows(const Streams<S>& in, int n_in, const float* __restrict__ W, int ldw,
                                           int jg, int lane, float (&acc)[S][8]) {
+  float2 a2[S][4];
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) acc[s][jj] = 0.f;
+    for (int q = 0; q < 4; ++q) a2[s][q] = make_float2(0.f, 0.f);
   const float* wrow = W + jg * 8;
-#pragma unroll 2
+#pragma unroll 4
   for (int i = 0; i < n_in; ++i) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw + 4));
+    const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w), wc = make_float2(w1.x, w1.y),
+                 wd = make_float2(w1.z, w1.w);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const float x = in.p[s][i * T + lane];
-      acc[s][0] = fmaf(x, w0.x, acc[s][0]);
-      acc[s][1] = fmaf(x, w0.y, acc[s][1]);
-      acc[s][2] = fmaf(x, w0.z, acc[s][2]);
-      acc[s][3] = fmaf(x, w0.w, acc[s][3]);
-      acc[s][4] = fmaf(x, w1.x, acc[s][4]);
-      acc[s][5] = fmaf(x, w1.y, acc[s][5]);
-      acc[s][6] = fmaf(x, w1.z, acc[s][6]);
-      acc[s][7] = fmaf(x, w1.w, acc[s][7]);
+      const float2 xx = make_float2(x, x);
+      a2[s][0] = ffma2(xx, wa, a2[s][0]);
+      a2[s][1] = ffma2(xx, wb, a2[s][1]);
+      a2[s][2] = ffma2(xx, wc, a2[s][2]);
+      a2[s][3] = ffma2(xx, wd, a2[s][3]);
     }
   }
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[s][2 * q] = a2[s][q].x;
+      acc[s][2 * q + 1] = a2[s][q].y;
+    }
 }
 
 // W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
@@ -108,11 +125,11 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
     __syncthreads();
     for (int task = crank * blockDim.x + threadIdx.x; task < nti * ntj; task += cs * blockDim.x) {
       const int ig = task / ntj, jg = task % ntj;
-      float acc[8][8];
+      float2 acc[8][4];
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
 #pragma unroll 4
       for (int p = 0; p < T; ++p) {
         const float4 h0 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8);
@@ -120,11 +137,13 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
         const float4 z0 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8);
         const float4 z1 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8 + 4);
         const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+        const float2 z[4] = {make_float2(z0.x, z0.y), make_float2(z0.z, z0.w), make_float2(z1.x, z1.y), make_float2(z1.z, z1.w)};
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a) {
+          const float2 hh = make_float2(h[a], h[a]);
 #pragma unroll
-          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(h[a], z[b], acc[a][b]);
+          for (int b = 0; b < 4; ++b) acc[a][b] = ffma2(hh, z[b], acc[a][b]);
+        }
       }
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
@@ -133,7 +152,7 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
             const int j = jg * 8 + b;
-            if (j < n_out) gW[(size_t)i * n_out + j] += acc[a][b];
+            if (j < n_out) gW[(size_t)i * n_out + j] += (b & 1) ? acc[a][b / 2].y : acc[a][b / 2].x;
           }
         }
       }
@@ -204,7 +223,7 @@ __device__ __forceinline__ void admm_one(const GenParams& g, float f, int64_t id
 }
 
 template <int S>
-__global__ void __launch_bounds__(GEN_THREADS) pinn_generic_kernel(const GenParams g) {
+__global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenParams g) {
   extern __shared__ float smem[];
   const NetDesc& net = g.net;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;

@@ -766,10 +766,18 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
     du = tu;
     df = tf;
   }
-  if (f_out)
+  if (h->fused.enabled) {
+    // forward-only mode of the fused kernel: u and f of every point in one pass (INF-L2:143-148 does two sess.runs)
+    LossCoef lc = make_loss_coef(h, PINN_LOSS_V4_MSE);
+    AdamFused none;
+    rc = fused_run(h->fused, h->net, lc, h->d_theta, dX, n, n, GEN_MODE_FORWARD, nullptr, nullptr, nullptr, 0, du, df, nullptr,
+                   nullptr, 0, 0.f, nullptr, none, nullptr, nullptr, h->stream, h->err);
+    h->launches += 1;
+  } else if (f_out) {
     rc = run_generic(h, h->S_res, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, df, 0, false, h->d_part, nullptr);
-  else
+  } else {
     rc = run_generic(h, 1, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, nullptr, 0, false, h->d_part_data, nullptr);
+  }
   if (rc == PINN_OK && !on_device) {
     cudaError_t e = cudaSuccess;
     if (u_out) e = cudaMemcpyAsync(u_out, tu, (size_t)n * no * sizeof(float), cudaMemcpyDeviceToHost, h->stream);

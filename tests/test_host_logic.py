@@ -111,3 +111,23 @@ def test_shard_range_partitions_exactly():
             assert f0 + c0 == f1
         assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
     assert data_weight(0) == 1.0 and data_weight(3) == 0.0
+
+
+def test_sweep_farm_replacement_runs_every_scenario_once_per_free_gpu():
+    from pinns_b200.sweep import get_combinations, schedule_runs
+    combos = get_combinations({"N_u": [100, 200], "N_f": [1000, 5000], "rho": [10.0]})
+    assert len(combos) == 4 and combos[0] == {"N_u": 100, "N_f": 1000, "rho": 10.0} and combos[-1]["N_f"] == 5000
+    launched = []
+
+    class FakeProc:
+        def __init__(self, argv):
+            launched.append(argv)
+            self.polls = 0
+
+        def poll(self):
+            self.polls += 1
+            return 0 if self.polls >= 2 else None
+
+    res = schedule_runs(["./Abgrall_ADMM.py"], combos, gpus=[0, 1], arg_order=["N_u", "N_f", "rho"], poll_s=0.0, popen=FakeProc)
+    assert len(launched) == 4 and launched[0] == ["./Abgrall_ADMM.py", "100", "1000", "10.0", "0"]
+    assert sorted(r["gpu"] for r in res) == [0, 0, 1, 1] and all(r["returncode"] == 0 for r in res)

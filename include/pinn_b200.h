@@ -62,6 +62,7 @@ typedef struct pinn_handle_s* pinn_handle_t;
 #define PINN_PATH_AUTO 0    /* fused thread-per-point kernel when the net qualifies, else generic */
 #define PINN_PATH_GENERIC 1 /* force the generic tiled FP32 kernel */
 #define PINN_PATH_FUSED 2   /* force the fused kernel (error if the net does not qualify) */
+#define PINN_PATH_TENSOR 3  /* tcgen05/TMEM 3xTF32 kernel for wide Burgers nets [2, n x k, 1], n in {32,64,96,128} */
 
 #define PINN_MAX_LAYERS 16
 
@@ -90,7 +91,7 @@ int pinn_synchronize(pinn_handle_t h);
 /* ---- introspection ---- */
 int pinn_num_params(pinn_handle_t h, int64_t* n_params);   /* P: weights + biases             */
 int pinn_packed_len(pinn_handle_t h, int64_t* n);          /* length of the packed vector below */
-int pinn_kernel_path(pinn_handle_t h, int32_t* path);      /* PINN_PATH_GENERIC or PINN_PATH_FUSED actually used */
+int pinn_kernel_path(pinn_handle_t h, int32_t* path);      /* PINN_PATH_GENERIC, _FUSED or _TENSOR actually used */
 int pinn_launch_count(pinn_handle_t h, int64_t* n);        /* kernels launched by this handle so far */
 
 /* ---- variables: tf.Variable init / assign / read (INF-L2:79-94, AB-ADMM:105-106) ---- */

@@ -14,7 +14,7 @@ PINN_MAX_LAYERS = 16
 
 PDE_BURGERS, PDE_EULER = 0, 1
 LOSS_V1_INF_L2, LOSS_V2_INF_ADMM, LOSS_V3_L1SQ, LOSS_V4_MSE, LOSS_V5_ADMM = 1, 2, 3, 4, 5
-PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_TENSOR = 0, 1, 2, 3
 NSUMS = 8
 SUM_DATA, SUM_RES, SUM_ABSF, SUM_MISFIT, SUM_F2 = 0, 1, 2, 3, 4
 

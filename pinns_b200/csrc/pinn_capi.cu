@@ -10,6 +10,7 @@
 
 #include "pinn_kernels.h"
 #include "pinn_fused.h"
+#include "pinn_tensor.h"
 
 struct pinn_handle_s {
   pinn_config_t cfg;
@@ -58,6 +59,8 @@ struct pinn_handle_s {
   bool l1_ready = false;
 
   FusedState fused;
+  TensorState tensor;
+  bool tensor_dirty = true;
 
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // pairs (before, after) of the dominant kernel
@@ -336,13 +339,14 @@ int pinn_create(const pinn_config_t* cfg, pinn_handle_t* out) {
   }
   rc = pinn_set_lambda(h, cfg->lambda1, cfg->lambda2);
   if (rc == PINN_OK) rc = fused_init(h->fused, h->net, h->cfg, h->num_sms, h->rvlen, h->err);
+  if (rc == PINN_OK) rc = tensor_init(h->tensor, h->net, h->cfg, h->num_sms, h->rvlen, h->err);
   if (rc != PINN_OK) {
     g_create_err = h->err;
     pinn_destroy(h);
     *out = nullptr;
     return rc;
   }
-  h->path_used = h->fused.enabled ? PINN_PATH_FUSED : PINN_PATH_GENERIC;
+  h->path_used = h->tensor.enabled ? PINN_PATH_TENSOR : (h->fused.enabled ? PINN_PATH_FUSED : PINN_PATH_GENERIC);
   return PINN_OK;
 }
 
@@ -350,6 +354,7 @@ int pinn_destroy(pinn_handle_t h) {
   if (!h) return PINN_OK;
   cudaSetDevice(h->cfg.device);
   fused_destroy(h->fused);
+  tensor_destroy(h->tensor);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
                    h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
@@ -399,7 +404,7 @@ int pinn_set_params(pinn_handle_t h, const float* theta, int on_device) {
   CK(cudaMemcpyAsync(h->d_theta, theta, (size_t)h->net.P * sizeof(float),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   if (!on_device) CK(cudaStreamSynchronize(h->stream));
-  h->weights_dirty = true;
+  h->weights_dirty = h->tensor_dirty = true;
   return PINN_OK;
 }
 
@@ -590,10 +595,28 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
                    with_data ? h->data_weight / (float)h->n_u : 0.f, h->d_packed, ad, e0, e1, h->stream, h->err);
     if (rc) return rc;
     h->launches += 2;
-    if (fuse_adam) h->weights_dirty = true;
+    if (fuse_adam) h->weights_dirty = h->tensor_dirty = true;
     return PINN_OK;
   }
   int grid = 0;
+  if (h->tensor.enabled) {
+    if (h->tensor_dirty) {
+      rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
+      if (rc) return rc;
+      h->tensor_dirty = false;
+      h->launches += 1;
+    }
+    if (e0) CK(cudaEventRecord(e0, h->stream));
+    rc = tensor_run(h->tensor, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
+                    h->nf_global > 0 ? h->nf_global : h->n_f, mode,
+                    (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
+                    state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, &grid, h->stream, h->err);
+    if (rc) return rc;
+    if (e1) CK(cudaEventRecord(e1, h->stream));
+    CK(pinn_finalize_launch(h->tensor.d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
+    h->launches += 2;
+    return PINN_OK;
+  }
   if (e0) CK(cudaEventRecord(e0, h->stream));
   rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state, h->d_part,
                    &grid);
@@ -660,6 +683,10 @@ int pinn_loss_grad(pinn_handle_t h, double* loss, float* grad_host) {
     CK(cudaMemcpyAsync(grad_host, h->d_packed, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  if (h->tensor.enabled) {
+    rc = tensor_check_hang(h->tensor, h->stream, h->err);
+    if (rc) return rc;
+  }
   if (loss) *loss = assemble_loss(h, sums);
   return PINN_OK;
 }
@@ -708,7 +735,7 @@ int pinn_adam_apply(pinn_handle_t h) {
   const int n = h->net.P + (h->cfg.trainable_lambda ? 2 : 0);
   CK(pinn_adam_launch(h->d_theta, h->d_packed, h->adam, n, adam_next_alpha(h), h->beta1, h->beta2, h->eps, h->stream));
   h->launches += 1;
-  h->weights_dirty = true;
+  h->weights_dirty = h->tensor_dirty = true;
   return PINN_OK;
 }
 
@@ -772,6 +799,15 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
     AdamFused none;
     rc = fused_run(h->fused, h->net, lc, h->d_theta, dX, n, n, GEN_MODE_FORWARD, nullptr, nullptr, nullptr, 0, du, df, nullptr,
                    nullptr, 0, 0.f, nullptr, none, nullptr, nullptr, h->stream, h->err);
+    h->launches += 1;
+  } else if (h->tensor.enabled && f_out) {
+    if (h->tensor_dirty) {
+      rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
+      h->tensor_dirty = false;
+    }
+    if (rc == PINN_OK)
+      rc = tensor_run(h->tensor, h->net, make_loss_coef(h, PINN_LOSS_V4_MSE), h->d_theta, dX, n, n, GEN_MODE_FORWARD, nullptr,
+                      nullptr, nullptr, 0, du, df, nullptr, h->stream, h->err);
     h->launches += 1;
   } else if (f_out) {
     rc = run_generic(h, h->S_res, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, df, 0, false, h->d_part, nullptr);

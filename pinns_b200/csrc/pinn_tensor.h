@@ -1,0 +1,22 @@
+// tcgen05 / TMEM kernel for wide Burgers nets (pinn_tensor.cu): host-side state and entry points.
+#pragma once
+#include <string>
+#include "pinn_kernels.h"
+
+struct TensorState {
+  bool enabled = false;
+  int n = 0, NL = 0, grid_max = 0, rvlen = 0;
+  size_t scratch_stride = 0;
+  float* d_scratch = nullptr;
+  float* d_wcan = nullptr;   // canonical hi/lo TF32 weight planes
+  float* d_part = nullptr;   // [grid][rvlen]
+  int* d_hang = nullptr;     // set by the kernel if an mbarrier wait times out
+};
+
+int tensor_init(TensorState& ts, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
+void tensor_destroy(TensorState& ts);
+int tensor_prep(TensorState& ts, const float* theta, cudaStream_t stream, std::string& err);
+int tensor_run(TensorState& ts, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n_pts,
+               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
+               float* f_out, int* grid_out, cudaStream_t stream, std::string& err);
+int tensor_check_hang(TensorState& ts, cudaStream_t stream, std::string& err);

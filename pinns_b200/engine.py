@@ -22,7 +22,7 @@ _LOSS = {
     "v4": capi.LOSS_V4_MSE, "v4_mse": capi.LOSS_V4_MSE, "euler_mse": capi.LOSS_V4_MSE,
     "v5": capi.LOSS_V5_ADMM, "v5_admm": capi.LOSS_V5_ADMM, "v6_euler_admm": capi.LOSS_V5_ADMM,
 }
-_PATH = {"auto": capi.PATH_AUTO, "generic": capi.PATH_GENERIC, "fused": capi.PATH_FUSED}
+_PATH = {"auto": capi.PATH_AUTO, "generic": capi.PATH_GENERIC, "fused": capi.PATH_FUSED, "tensor": capi.PATH_TENSOR}
 
 
 def _is_torch_tensor(a) -> bool:
@@ -103,7 +103,7 @@ class Engine:
     def kernel_path(self) -> str:
         p = C.c_int32()
         self._ck(capi.lib.pinn_kernel_path(self._h, C.byref(p)), "pinn_kernel_path")
-        return {capi.PATH_GENERIC: "generic", capi.PATH_FUSED: "fused"}[p.value]
+        return {capi.PATH_GENERIC: "generic", capi.PATH_FUSED: "fused", capi.PATH_TENSOR: "tensor"}[p.value]
 
     @property
     def launch_count(self) -> int:

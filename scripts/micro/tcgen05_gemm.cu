@@ -151,6 +151,120 @@ __global__ void __launch_bounds__(128, 1) gemm_kernel(const float* __restrict__ 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(N < 32 ? 32 : N));
 }
 
+// MN-major operands: At is [K x 128] (element (k, m)), Bt is [K x N] (element (k, n)), staged as core matrices of
+// 8 k-rows x 16 B (4 consecutive m / n), i.e. exactly the tile a K-major consumer of the transposed data would read.
+// VARIANT selects how LBO / SBO are interpreted for the MN-major descriptor.
+template <int N, int VARIANT>
+__global__ void __launch_bounds__(128, 1) gemm_mn_kernel(const float* __restrict__ At, const float* __restrict__ Bt,
+                                                         float* __restrict__ D, int K, int* status) {
+  extern __shared__ __align__(128) float smem[];
+  float* sA = smem;            // [K x 128] canonical with rows = k
+  float* sB = sA + K * M;      // [K x N]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int idx = tid; idx < K * M; idx += blockDim.x) sA[canon_off(idx / M, idx % M, M)] = At[idx];
+  for (int idx = tid; idx < K * N; idx += blockDim.x) sB[canon_off(idx / N, idx % N, N)] = Bt[idx];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(N < 32 ? 32 : N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(M, N) | (1u << 15) | (1u << 16);   // a_major = b_major = MN
+    // tile geometry: core matrices (8 k x 4 mn) are 128 B; next core matrix along MN: +128 B; next 8-k group: +(MN/4)*128 B
+    const uint32_t a_mn = 128, a_k = (M / 4) * 128, b_mn = 128, b_k = (N / 4) * 128;
+    uint32_t accum = 0;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint64_t da, db;
+      if (VARIANT == 0) {  // LBO = MN stride, SBO = K stride
+        da = make_desc(smem_u32(sA) + (k0 / 8) * a_k, a_mn, a_k);
+        db = make_desc(smem_u32(sB) + (k0 / 8) * b_k, b_mn, b_k);
+      } else {             // LBO = K stride, SBO = MN stride
+        da = make_desc(smem_u32(sA) + (k0 / 8) * a_k, a_k, a_mn);
+        db = make_desc(smem_u32(sB) + (k0 / 8) * b_k, b_k, b_mn);
+      }
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+          : "memory");
+      accum = 1;
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+  }
+  bool done = false;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    if (mbar_try_wait(&bar, 0)) { done = true; break; }
+  }
+  if (!done && tid == 0) *status = 1;
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (done) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int row = warp * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < N) D[row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(N < 32 ? 32 : N));
+}
+
+template <int N, int VARIANT>
+int run_mn(int K) {
+  std::vector<float> A(K * M), B(K * N), D(M * N, 0.f);
+  srand(2);
+  for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+  for (auto& x : B) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+  float *dA, *dB, *dD; int* dS;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dS, 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, D.size() * 4); cudaMemset(dS, 0, 4);
+  const size_t smem = (size_t)(K * M + K * N) * 4;
+  cudaFuncSetAttribute(gemm_mn_kernel<N, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gemm_mn_kernel<N, VARIANT><<<1, 128, smem>>>(dA, dB, dD, K, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  int st = 0;
+  cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0, maxref = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k) ref += (double)A[k * M + m] * (double)B[k * N + n];
+      maxerr = fmax(maxerr, fabs(ref - D[m * N + n]));
+      maxref = fmax(maxref, fabs(ref));
+    }
+  printf("MN-major N=%3d K=%3d variant=%d : cuda=%s status=%d  max|err|=%.3e  max|ref|=%.3f  rel=%.2e\n", N, K, VARIANT,
+         cudaGetErrorString(e), st, maxerr, maxref, maxerr / maxref);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
+  return (e == cudaSuccess && st == 0) ? 0 : 1;
+}
+
 template <int N, bool SPLIT>
 int run(int K) {
   std::vector<float> A(M * K), B(N * K), D(M * N, 0.f);
@@ -188,7 +302,11 @@ int main() {
   bad += run<32, false>(32);
   bad += run<32, true>(32);
   bad += run<128, false>(64);
-  bad += run<128, true>(128);
+  bad += run<128, true>(48);
+  bad += run_mn<64, 0>(32);
+  bad += run_mn<64, 1>(32);
+  bad += run_mn<128, 0>(64);
+  bad += run_mn<128, 1>(64);
   bad += run<64, true>(24);
   return bad;
 }

@@ -4,8 +4,8 @@ sys.path.insert(0, '/root/repo')
 from pinns_b200 import Engine
 from tests.helpers import rand_theta
 
-def run(name, layers, pde, loss, n_u, n_f, steps=20, fpp=None):
-    eng = Engine(layers, [-1, 0], [1, 0.99], pde=pde, loss=loss, lambda2=0.01 / np.pi, rho=40.0)
+def run(name, layers, pde, loss, n_u, n_f, steps=20, fpp=None, path='auto'):
+    eng = Engine(layers, [-1, 0], [1, 0.99], pde=pde, loss=loss, lambda2=0.01 / np.pi, rho=40.0, path=path)
     eng.use_torch_stream()
     eng.set_params(rand_theta(layers, np.random.default_rng(0)))
     rng = np.random.default_rng(1)
@@ -27,3 +27,8 @@ run('config3 euler200x5 N=1000', [2] + [200] * 5 + [3], 'euler', 'v5', 200, 1000
 run('euler200x5 N=65536', [2] + [200] * 5 + [3], 'euler', 'v5', 200, 65536, 5, 2895600)
 run('config5 burgers128 N=262144', [2] + [128] * 8 + [1], 'burgers', 'v4', 100, 262144, 3, 2759680)
 run('burgers200x8 N=1000 (AB-L2)', [2] + [200] * 8 + [1], 'burgers', 'v4', 100, 1000, 50, 6731200)
+run('config5 burgers128 N=262144 TENSOR', [2] + [128] * 8 + [1], 'burgers', 'v4', 100, 262144, 3, 2759680, path='tensor')
+run('burgers128 N=2M TENSOR', [2] + [128] * 8 + [1], 'burgers', 'v4', 100, 1 << 21, 2, 2759680, path='tensor')
+run('burgers128 N=1000 TENSOR', [2] + [128] * 8 + [1], 'burgers', 'v4', 100, 1000, 20, 2759680, path='tensor')
+run('burgers64x8 N=262144 TENSOR', [2] + [64] * 8 + [1], 'burgers', 'v4', 100, 262144, 3, None, path='tensor')
+run('burgers64x8 N=262144 generic', [2] + [64] * 8 + [1], 'burgers', 'v4', 100, 262144, 3, None, path='generic')

@@ -599,7 +599,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
     return PINN_OK;
   }
   int grid = 0;
-  if (h->tensor.enabled) {
+  if (h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS)) {
     if (h->tensor_dirty) {
       rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
       if (rc) return rc;
@@ -800,7 +800,7 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
     rc = fused_run(h->fused, h->net, lc, h->d_theta, dX, n, n, GEN_MODE_FORWARD, nullptr, nullptr, nullptr, 0, du, df, nullptr,
                    nullptr, 0, 0.f, nullptr, none, nullptr, nullptr, h->stream, h->err);
     h->launches += 1;
-  } else if (h->tensor.enabled && f_out) {
+  } else if (h->tensor.enabled && f_out && (h->tensor.forced || n >= TENSOR_MIN_POINTS)) {
     if (h->tensor_dirty) {
       rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
       h->tensor_dirty = false;

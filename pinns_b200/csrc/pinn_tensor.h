@@ -5,6 +5,7 @@
 
 struct TensorState {
   bool enabled = false;
+  bool forced = false;       // PINN_PATH_TENSOR: use it whatever the batch size
   int n = 0, NL = 0, grid_max = 0, rvlen = 0;
   size_t scratch_stride = 0;
   float* d_scratch = nullptr;
@@ -12,6 +13,10 @@ struct TensorState {
   float* d_part = nullptr;   // [grid][rvlen]
   int* d_hang = nullptr;     // set by the kernel if an mbarrier wait times out
 };
+
+// AUTO uses the tensor kernel from this many points on: below it the job has fewer 128-point tiles than the GPU has SMs
+// and the generic kernel (clusters of CTAs per 32-point tile) is faster
+constexpr int64_t TENSOR_MIN_POINTS = 8192;
 
 int tensor_init(TensorState& ts, const NetDesc& net, const pinn_config_t& cfg, int num_sms, int rvlen, std::string& err);
 void tensor_destroy(TensorState& ts);

@@ -105,28 +105,31 @@ def e2e_schedule(full=False):
     return g, layers, theta0, prob, dict(adam_steps=1500, lbfgs={'maxiter': 400, 'maxfun': 600, 'maxcor': 50, 'maxls': 50, 'ftol': 1e-9})
 
 
-def save_e2e(full=False):
+def save_e2e(full=False, fp32=False):
     import torch
     from oracle.optim import lbfgs_minimize
     torch.set_num_threads(6)
     g, layers, theta0, prob, sched = e2e_schedule(full)
+    dt = torch.float32 if fp32 else torch.float64   # fp32 = the arithmetic of the reference's TF graph itself
     theta = theta0.astype(np.float64)
     opt = TF1Adam(theta.size)
     for it in range(sched["adam_steps"]):
-        ev = tg.evaluate(theta, prob, g["X_u"], g["u"], g["X_f"])
+        ev = tg.evaluate(theta, prob, g["X_u"], g["u"], g["X_f"], dtype=dt)
         theta = opt.step(theta, ev.grad)
     u_adam, _ = tg.predict(theta, prob, g["X_star"])
     err_adam = tg.relative_l2(g["u_star"], u_adam)
     loss_adam = tg.evaluate(theta, prob, g["X_u"], g["u"], g["X_f"], want_grad=False).loss
 
     def fun(x):
-        e = tg.evaluate(x, prob, g["X_u"], g["u"], g["X_f"])
+        e = tg.evaluate(x, prob, g["X_u"], g["u"], g["X_f"], dtype=dt)
         return e.loss, e.grad
     theta, res = lbfgs_minimize(fun, theta, sched["lbfgs"])
     u_fin, _ = tg.predict(theta, prob, g["X_star"])
     out = {"error_u_after_adam": err_adam, "loss_after_adam": loss_adam, "error_u_final": tg.relative_l2(g["u_star"], u_fin),
            "loss_final": float(res.fun), "lbfgs_nit": int(res.nit), "lbfgs_nfev": int(res.nfev)}
-    json.dump(out, open(os.path.join(HERE, "e2e_burgers_inference%s.json" % ("_full" if full else "")), "w"), indent=1)
+    out["oracle_dtype"] = "float32" if fp32 else "float64"
+    out["lbfgs_message"] = str(res.message)
+    json.dump(out, open(os.path.join(HERE, "e2e_burgers_inference%s%s.json" % ("_full" if full else "", "_fp32" if fp32 else "")), "w"), indent=1)
     print("e2e", out)
 
 
@@ -140,3 +143,5 @@ if __name__ == "__main__":
         save_e2e()
     if "e2e_full" in what:
         save_e2e(True)
+    if "e2e_full_fp32" in what:
+        save_e2e(True, fp32=True)

@@ -64,31 +64,72 @@ __device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const fl
   return *reinterpret_cast<float2*>(&d);
 }
 
-// acc[s][jj] = sum_i in_s[i][lane] * W[i][8*jg + jj]
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// rows [k0, k0+kc) of all S input streams -> act[s][i][32 points] (asynchronous; the caller waits)
 template <int S>
-__device__ __forceinline__ void gemm_rows(const Streams<S>& in, int n_in, const float* __restrict__ W, int ldw,
-                                          int jg, int lane, float (&acc)[S][8]) {
+__device__ __forceinline__ void stage_act(const Streams<S>& in, int k0, int kc, float* act, int kch) {
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    for (int idx = threadIdx.x; idx < kc * 8; idx += blockDim.x) {
+      const int i = idx >> 3, c = idx & 7;
+      cp_async16(act + (s * kch + i) * T + c * 4, in.p[s] + (size_t)(k0 + i) * T + c * 4);
+    }
+}
+
+// acc[s][jj] = sum_i in_s[i][lane] * W[i][8*jg + jj].  Operands are staged in shared memory with cp.async, K chunk by
+// K chunk (one chunk unless the net is wider than the shared-memory budget): the input rows by the whole CTA, the
+// 8-column weight slice of output group jg by the warp that owns it, so one L2 round trip feeds a whole chunk instead
+// of one per unrolled iteration.  Called by every thread of the CTA (it contains CTA barriers); `active` warps compute.
+// act_ready: the single chunk of inputs is already in flight / resident in `act` (later rounds, or pre-staged).
+template <int S>
+__device__ __forceinline__ void gemm_staged(const Streams<S>& in, int n_in, const float* __restrict__ W, int ldw, int jg,
+                                            bool active, bool act_ready, float* act, float* wsl, int kch, int lane,
+                                            float (&acc)[S][8]) {
   float2 a2[S][4];
 #pragma unroll
   for (int s = 0; s < S; ++s)
 #pragma unroll
     for (int q = 0; q < 4; ++q) a2[s][q] = make_float2(0.f, 0.f);
-  const float* wrow = W + jg * 8;
-#pragma unroll 4
-  for (int i = 0; i < n_in; ++i) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)i * ldw + 4));
-    const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w), wc = make_float2(w1.x, w1.y),
-                 wd = make_float2(w1.z, w1.w);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const float x = in.p[s][i * T + lane];
-      const float2 xx = make_float2(x, x);
-      a2[s][0] = ffma2(xx, wa, a2[s][0]);
-      a2[s][1] = ffma2(xx, wb, a2[s][1]);
-      a2[s][2] = ffma2(xx, wc, a2[s][2]);
-      a2[s][3] = ffma2(xx, wd, a2[s][3]);
+  const bool single = n_in <= kch;
+  for (int k0 = 0; k0 < n_in; k0 += kch) {
+    const int kc = min(kch, n_in - k0);
+    if (!(single && act_ready)) stage_act<S>(in, k0, kc, act, kch);
+    if (active) {
+      const float* wsrc = W + (size_t)k0 * ldw + jg * 8;
+      for (int idx = lane; idx < kc * 2; idx += 32) {
+        const int row = idx >> 1, half = idx & 1;
+        cp_async16(wsl + row * 8 + half * 4, wsrc + (size_t)row * ldw + half * 4);
+      }
     }
+    cp_async_wait_all();
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int i = 0; i < kc; ++i) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wsl + i * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsl + i * 8 + 4);
+        const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w), wc = make_float2(w1.x, w1.y),
+                     wd = make_float2(w1.z, w1.w);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float x = act[(s * kch + i) * T + lane];
+          const float2 xx = make_float2(x, x);
+          a2[s][0] = ffma2(xx, wa, a2[s][0]);
+          a2[s][1] = ffma2(xx, wb, a2[s][1]);
+          a2[s][2] = ffma2(xx, wc, a2[s][2]);
+          a2[s][3] = ffma2(xx, wd, a2[s][3]);
+        }
+      }
+    }
+    if (single) __syncwarp();  // the weight slice is warp private
+    else __syncthreads();      // the next chunk overwrites act
   }
 #pragma unroll
   for (int s = 0; s < S; ++s)
@@ -102,7 +143,7 @@ __device__ __forceinline__ void gemm_rows(const Streams<S>& in, int n_in, const 
 // W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
 template <int S>
 __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const float* zb, int l, float* gp, float* smem,
-                            int crank, int cs) {
+                            int crank, int cs, bool first) {
   const int n_in = g.net.n[l], n_out = g.net.n[l + 1];
   const int np_in = g.net.np[l], np_out = g.net.np[l + 1];
   const int ldh = np_in + 4, ldz = np_out + 4;
@@ -111,25 +152,33 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
   const int nti = np_in / 8, ntj = np_out / 8;
   float* gW = gp + g.net.w_off[l];
   float* gb = gp + g.net.b_off[l];
+  const int ntasks = nti * ntj;
+  const bool one_task = ntasks <= cs * (int)blockDim.x;  // then the 8x8 accumulator tile lives across the stream loop
+  float2 acc[8][4];
   for (int s = 0; s < S; ++s) {
     __syncthreads();
+    // transposing 4-byte cp.async: every element of both operands is in flight at once (one L2 round trip per stream)
     for (int idx = threadIdx.x; idx < np_in * T; idx += blockDim.x) {
       const int i = idx / T, p = idx % T;
-      Hs[p * ldh + i] = (i < n_in) ? hin.p[s][i * T + p] : 0.f;
+      if (i < n_in) cp_async4(Hs + p * ldh + i, hin.p[s] + i * T + p);
+      else Hs[p * ldh + i] = 0.f;
     }
     const float* zsrc = zb + (size_t)s * g.net.npmax * T;
     for (int idx = threadIdx.x; idx < np_out * T; idx += blockDim.x) {
       const int j = idx / T, p = idx % T;
-      Zs[p * ldz + j] = (j < n_out) ? zsrc[j * T + p] : 0.f;
+      if (j < n_out) cp_async4(Zs + p * ldz + j, zsrc + j * T + p);
+      else Zs[p * ldz + j] = 0.f;
     }
+    cp_async_wait_all();
     __syncthreads();
-    for (int task = crank * blockDim.x + threadIdx.x; task < nti * ntj; task += cs * blockDim.x) {
+    for (int task = crank * blockDim.x + threadIdx.x; task < ntasks; task += cs * blockDim.x) {
       const int ig = task / ntj, jg = task % ntj;
-      float2 acc[8][4];
+      if (!one_task || s == 0) {
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
+          for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
+      }
 #pragma unroll 4
       for (int p = 0; p < T; ++p) {
         const float4 h0 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8);
@@ -145,15 +194,20 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
           for (int b = 0; b < 4; ++b) acc[a][b] = ffma2(hh, z[b], acc[a][b]);
         }
       }
+      if (one_task && s < S - 1) continue;  // keep accumulating over the streams in registers
+      // the partial row starts at zero: plain stores on the first visit, else one batch of 8 loads per row
+      const bool plain = first && (one_task || s == 0);
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         const int i = ig * 8 + a;
         if (i < n_in) {
+          float* row = gW + (size_t)i * n_out + jg * 8;
+          float old[8];
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int j = jg * 8 + b;
-            if (j < n_out) gW[(size_t)i * n_out + j] += (b & 1) ? acc[a][b / 2].y : acc[a][b / 2].x;
-          }
+          for (int b = 0; b < 8; ++b) old[b] = (!plain && jg * 8 + b < n_out) ? row[b] : 0.f;
+#pragma unroll
+          for (int b = 0; b < 8; ++b)
+            if (jg * 8 + b < n_out) row[b] = old[b] + ((b & 1) ? acc[a][b / 2].y : acc[a][b / 2].x);
         }
       }
     }
@@ -162,7 +216,7 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
         float sum = 0.f;
 #pragma unroll 8
         for (int p = 0; p < T; ++p) sum += Zs[p * ldz + j];
-        gb[j] += sum;
+        gb[j] = first ? sum : gb[j] + sum;
       }
     }
   }
@@ -233,6 +287,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
   float* gp = g.part + (size_t)blockIdx.x * g.rvlen;
   const bool backward = (g.mode != GEN_MODE_FORWARD);
   const int L = net.L;
+  // shared memory: act [S][kch][32] (GEMM inputs) | { per-warp weight slices [nwarps][kch][8]  or  the weight-gradient
+  // staging tiles } (never live at the same time)
+  const int kch = g.kch;
+  float* act = smem;
+  float* gst = smem + S * kch * T;
+  float* wsl = gst + warp * kch * 8;
+  const int per_round = cs * nwarps;
 
   for (int k = threadIdx.x; k < g.rvlen; k += blockDim.x) gp[k] = 0.f;
   float cB = g.lc.cB;
@@ -245,6 +306,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
   __syncthreads();
 
   const int64_t ntiles = (g.N + T - 1) / T;
+  bool first = true;
   for (int64_t tile = cid; tile < ntiles; tile += nclusters) {
     const int64_t pidx = tile * T + lane;
     const bool valid = pidx < g.N;
@@ -279,9 +341,13 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
       const float* W = g.wp + net.wp_off[l];
       const float* b = g.theta + net.b_off[l];
       const bool head = (l == L - 1);
-      for (int jg = crank * nwarps + warp; jg < np_out / 8; jg += cs * nwarps) {
+      const int ngroups = np_out / 8;
+      for (int r = 0; r * per_round < ngroups; ++r) {
+        const int jg = (r * cs + crank) * nwarps + warp;
+        const bool active = jg < ngroups;
         float acc[S][8];
-        gemm_rows<S>(in, n_in, W, np_out, jg, lane, acc);
+        gemm_staged<S>(in, n_in, W, np_out, jg, active, r > 0, act, wsl, kch, lane, acc);
+        if (!active) continue;
         if (!head) {
           float* blk = scr + g.sd.hid[l];
 #pragma unroll
@@ -406,19 +472,25 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
     for (int l = L - 1; l >= 0; --l) {
       const float* zb = scr + g.sd.zb[cur];
       const Streams<S> hin = layer_inputs<S>(g, scr, l);
-      weight_grad<S>(g, hin, zb, l, gp, smem, crank, cs);
-      if (l > 0) {
-        Streams<S> zin;
+      Streams<S> zin;
 #pragma unroll
-        for (int s = 0; s < S; ++s) zin.p[s] = zb + (size_t)s * net.npmax * T;
+      for (int s = 0; s < S; ++s) zin.p[s] = zb + (size_t)s * net.npmax * T;
+      const bool prestage = (l > 0) && (net.n[l + 1] <= kch);
+      if (prestage) stage_act<S>(zin, 0, net.n[l + 1], act, kch);  // lands while the weight gradient runs
+      weight_grad<S>(g, hin, zb, l, gp, gst, crank, cs, first);
+      if (l > 0) {
         const int n_j = net.n[l + 1], np_i = net.np[l];
         const float* WT = g.wt + net.wt_off[l];
         const float* blk = scr + g.sd.hid[l - 1];
         float* zn = scr + g.sd.zb[cur ^ 1];
         const int ldz = net.npmax * T;
-        for (int ig = crank * nwarps + warp; ig < np_i / 8; ig += cs * nwarps) {
+        const int ngroups = np_i / 8;
+        for (int r = 0; r * per_round < ngroups; ++r) {
+          const int ig = (r * cs + crank) * nwarps + warp;
+          const bool active = ig < ngroups;
           float acc[S][8];
-          gemm_rows<S>(zin, n_j, WT, np_i, ig, lane, acc);
+          gemm_staged<S>(zin, n_j, WT, np_i, ig, active, prestage || r > 0, act, wsl, kch, lane, acc);
+          if (!active) continue;
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) {
             const int i = ig * 8 + ii;
@@ -453,6 +525,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
       }
     }
     cur = 0;
+    first = false;
   }
 
   // ---- per-CTA partial sums ----
@@ -472,10 +545,24 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
 
 }  // namespace
 
-size_t pinn_generic_smem_bytes(const NetDesc& net) { return (size_t)T * (2 * net.npmax + 8) * sizeof(float); }
+// shared memory of one CTA and the K chunk it allows: act [S][kch][T] + max(weight slices [warps][kch][8], weight-gradient
+// staging [T][2 npmax + 8]); kch covers the widest layer unless that would pass ~216 KB
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, int* kch_out) {
+  const size_t gsz = (size_t)T * (2 * net.npmax + 8);
+  const size_t budget = 216 * 1024 / sizeof(float);
+  int kch = net.npmax;
+  auto total = [&](int k) {
+    const size_t w = (size_t)(GEN_THREADS / 32) * k * 8;
+    return (size_t)S * k * T + (w > gsz ? w : gsz);
+  };
+  while (kch > 8 && total(kch) > budget) kch -= 8;
+  if (kch_out) *kch_out = kch;
+  return total(kch) * sizeof(float);
+}
 
-cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream) {
-  const size_t smem = pinn_generic_smem_bytes(g.net);
+cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStream_t stream) {
+  GenParams g = g_in;
+  const size_t smem = pinn_generic_smem_bytes(g.net, S, &g.kch);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

@@ -35,9 +35,10 @@ struct GenParams {
   float* part;          // [grid][rvlen] per-CTA partial packed vectors
   int rvlen;
   int cluster;          // CTAs per 32-point tile (1, 2, 4 or 8); grid = clusters * cluster
+  int kch;              // K rows staged per shared-memory chunk (set by pinn_generic_launch)
 };
 
-size_t pinn_generic_smem_bytes(const NetDesc& net);
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, int* kch_out);
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream);
 
 // small kernels (pinn_aux.cu)

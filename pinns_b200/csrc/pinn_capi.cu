@@ -158,14 +158,8 @@ static int gen_grid_for(const pinn_handle_s* h, int64_t n, int* cluster) {
   return (int)(clusters * cs);
 }
 
-// one launch of the generic kernel; returns the grid used through *grid_out
-static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
-                       float* u_out, float* f_out, int admm_op, bool use_state, float* part, int* grid_out) {
-  {
-    int rcw = ensure_weights(h);  // padded / transposed weight copies are only needed by this kernel
-    if (rcw) return rcw;
-  }
-  GenParams g;
+static void fill_gen_params(const pinn_handle_s* h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
+                            float* u_out, float* f_out, int admm_op, bool use_state, float* part, GenParams& g) {
   memset(&g, 0, sizeof(g));
   g.net = h->net;
   g.lc = make_loss_coef(h, loss);
@@ -187,10 +181,49 @@ static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* 
   g.scratch = h->d_scratch;
   g.part = part;
   g.rvlen = h->rvlen;
+}
+
+// one launch of the generic kernel; returns the grid used through *grid_out.  u_data != null (S == 1): the squared
+// data misfit and its adjoint are formed inside the kernel
+static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
+                       float* u_out, float* f_out, int admm_op, bool use_state, float* part, int* grid_out,
+                       const float* u_data = nullptr) {
+  {
+    int rcw = ensure_weights(h);  // padded / transposed weight copies are only needed by this kernel
+    if (rcw) return rcw;
+  }
+  GenParams g;
+  fill_gen_params(h, S, mode, loss, X, n, seed, u_out, f_out, admm_op, use_state, part, g);
+  g.u_data = u_data;
+  g.data_c = h->n_u > 0 ? h->data_weight / (float)h->n_u : 0.f;
   const int grid = gen_grid_for(h, n, &g.cluster);
   CK(pinn_generic_launch(g, S, grid, h->stream));
   h->launches += 1;
   if (grid_out) *grid_out = grid;
+  return PINN_OK;
+}
+
+// residual tiles and the (squared) data term in ONE launch of the generic kernel: the data CTAs follow the residual
+// CTAs in the grid, in the partial-sum rows and in the scratch slabs
+static int run_generic_dual(pinn_handle_t h, int loss, int admm_op, bool use_state, int* rows_out) {
+  int rcw = ensure_weights(h);
+  if (rcw) return rcw;
+  GenParams g, gd;
+  fill_gen_params(h, h->S_res, GEN_MODE_TRAIN, loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, use_state, h->d_part, g);
+  const int grid_res = gen_grid_for(h, h->n_f, &g.cluster);
+  const int cs = g.cluster;
+  int64_t dtiles = (h->n_u + PINN_TILE - 1) / PINN_TILE;
+  if (dtiles > h->gen_grid_max / cs) dtiles = h->gen_grid_max / cs;
+  const int grid_data = (int)dtiles * cs;
+  fill_gen_params(h, 1, GEN_MODE_TRAIN, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, nullptr, nullptr, nullptr, 0, false,
+                  h->d_part + (size_t)grid_res * h->rvlen, gd);
+  gd.u_data = h->d_u;
+  gd.data_c = h->data_weight / (float)h->n_u;
+  gd.cluster = cs;
+  gd.scratch = h->d_scratch + (size_t)(grid_res / cs) * h->sd_res.total;
+  CK(pinn_generic_dual_launch(g, h->S_res, grid_res, gd, grid_data, h->stream));
+  h->launches += 1;
+  *rows_out = grid_res + grid_data;
   return PINN_OK;
 }
 
@@ -318,9 +351,9 @@ int pinn_create(const pinn_config_t* cfg, pinn_handle_t* out) {
   if ((e = cudaMalloc(&h->d_wt, (size_t)wt * sizeof(float))) != cudaSuccess) return fail("cudaMalloc wt", e);
   if ((e = cudaMalloc(&h->d_packed, (size_t)h->rvlen * sizeof(float))) != cudaSuccess) return fail("cudaMalloc packed", e);
   if ((e = cudaMemset(h->d_packed, 0, (size_t)h->rvlen * sizeof(float))) != cudaSuccess) return fail("cudaMemset", e);
-  if ((e = cudaMalloc(&h->d_scratch, (size_t)h->sd_res.total * h->gen_grid_max * sizeof(float))) != cudaSuccess)
+  if ((e = cudaMalloc(&h->d_scratch, (size_t)h->sd_res.total * h->gen_grid_max * 2 * sizeof(float))) != cudaSuccess)
     return fail("cudaMalloc scratch", e);
-  if ((e = cudaMalloc(&h->d_part, (size_t)h->rvlen * h->gen_grid_max * sizeof(float))) != cudaSuccess)
+  if ((e = cudaMalloc(&h->d_part, (size_t)h->rvlen * h->gen_grid_max * 2 * sizeof(float))) != cudaSuccess)
     return fail("cudaMalloc partials", e);
   if ((e = cudaMalloc(&h->d_part_data, (size_t)h->rvlen * h->gen_grid_max * sizeof(float))) != cudaSuccess)
     return fail("cudaMalloc data partials", e);
@@ -522,6 +555,15 @@ static int data_term(pinn_handle_t h, bool want_grad) {
     CK(cudaMemsetAsync(h->d_data_loss, 0, sizeof(float), h->stream));
     return PINN_OK;
   }
+  if (want_grad && h->cfg.loss != PINN_LOSS_V1_INF_L2) {  // squared misfit: seed and loss inside the kernel, one pass
+    int grid = 0;
+    int rc1 = run_generic(h, 1, GEN_MODE_TRAIN, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, nullptr, nullptr, nullptr, 0, false,
+                          h->d_part_data, &grid, h->d_u);
+    if (rc1) return rc1;
+    CK(pinn_finalize_launch(h->d_part_data, grid, h->rvlen, h->d_packed, 1, nullptr, -1, h->stream));
+    h->launches += 1;
+    return PINN_OK;
+  }
   int rc = run_generic(h, 1, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, nullptr, h->d_upred, nullptr, 0, false,
                        h->d_part_data, nullptr);
   if (rc) return rc;
@@ -555,6 +597,13 @@ static int timing_event(pinn_handle_t h, cudaEvent_t* out) {
 // the squared data term rides inside the fused kernel (extra batches); V1's un-squared norm needs ||r|| first
 static bool fused_handles_data(const pinn_handle_s* h) {
   return h->fused.enabled && h->cfg.loss != PINN_LOSS_V1_INF_L2 && h->n_u > 0 && h->data_weight != 0.0f;
+}
+
+// same for the generic kernel's training pass (dual launch) when neither the fused nor the tensor kernel takes the batch
+static bool generic_handles_data(const pinn_handle_s* h) {
+  if (h->fused.enabled) return false;
+  if (h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS)) return false;
+  return h->cfg.loss != PINN_LOSS_V1_INF_L2 && h->n_u > 0 && h->data_weight != 0.0f;
 }
 
 static float adam_next_alpha(pinn_handle_s* h) {
@@ -618,8 +667,11 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
     return PINN_OK;
   }
   if (e0) CK(cudaEventRecord(e0, h->stream));
-  rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state, h->d_part,
-                   &grid);
+  if (mode == GEN_MODE_TRAIN && generic_handles_data(h))
+    rc = run_generic_dual(h, h->cfg.loss, admm_op, state, &grid);
+  else
+    rc = run_generic(h, h->S_res, mode, h->cfg.loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, state, h->d_part,
+                     &grid);
   if (rc) return rc;
   if (e1) CK(cudaEventRecord(e1, h->stream));
   CK(pinn_finalize_launch(h->d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
@@ -652,7 +704,7 @@ int pinn_loss_grad_device(pinn_handle_t h) {
   rc = residual_pass(h, GEN_MODE_TRAIN, 0);
   if (rc) return rc;
   h->l1_ready = false;
-  if (fused_handles_data(h)) return PINN_OK;
+  if (fused_handles_data(h) || generic_handles_data(h)) return PINN_OK;
   return data_term(h, true);
 }
 

@@ -276,15 +276,15 @@ __device__ __forceinline__ void admm_one(const GenParams& g, float f, int64_t id
   g.gamma[idx] = gg + rho * (f - znew);
 }
 
+// the work of CTA `bid` of `nblk` on job g (a launch may carry two jobs: residual tiles and data-term tiles)
 template <int S>
-__global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenParams g) {
-  extern __shared__ float smem[];
+__device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nblk, float* smem) {
   const NetDesc& net = g.net;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int cs = g.cluster;                       // CTAs per tile
-  const int crank = blockIdx.x % cs, cid = blockIdx.x / cs, nclusters = gridDim.x / cs;
+  const int crank = bid % cs, cid = bid / cs, nclusters = nblk / cs;
   float* scr = g.scratch + (size_t)cid * g.sd.total;
-  float* gp = g.part + (size_t)blockIdx.x * g.rvlen;
+  float* gp = g.part + (size_t)bid * g.rvlen;
   const bool backward = (g.mode != GEN_MODE_FORWARD);
   const int L = net.L;
   // shared memory: act [S][kch][32] (GEMM inputs) | { per-warp weight slices [nwarps][kch][8]  or  the weight-gradient
@@ -396,6 +396,11 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
           if (o < net.n_out && valid) {
             if (g.u_out) g.u_out[pidx * net.n_out + o] = Y[o * T + lane];
             if (g.seed) sd = g.seed[pidx * net.n_out + o];
+            if (g.u_data) {  // squared misfit data_c * sum (u^ - u)^2 in one pass (all losses but INF-L2's norm)
+              const float r = Y[o * T + lane] - g.u_data[pidx * net.n_out + o];
+              sd = 2.0f * g.data_c * r;
+              ps.v[PINN_SUM_DATA] += g.data_c * r * r;
+            }
           }
           zb[o * T + lane] = sd;
         }
@@ -543,6 +548,22 @@ __global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const GenP
   }
 }
 
+template <int S>
+__global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const __grid_constant__ GenParams g) {
+  extern __shared__ float smem[];
+  generic_body<S>(g, blockIdx.x, gridDim.x, smem);
+}
+
+// residual tiles (CTAs [0, grid_res)) and data-term tiles (the rest) in one launch: at the reference's batch sizes
+// neither job fills the GPU, and one launch + one partial-sum reduction replaces two of each
+template <int S>
+__global__ void __launch_bounds__(GEN_THREADS, 2)
+    pinn_generic_dual_kernel(const __grid_constant__ GenParams g, const __grid_constant__ GenParams gd, int grid_res) {
+  extern __shared__ float smem[];
+  if ((int)blockIdx.x < grid_res) generic_body<S>(g, blockIdx.x, grid_res, smem);
+  else generic_body<1>(gd, blockIdx.x - grid_res, gridDim.x - grid_res, smem);
+}
+
 }  // namespace
 
 // shared memory of one CTA and the K chunk it allows: act [S][kch][T] + max(weight slices [warps][kch][8], weight-gradient
@@ -585,6 +606,42 @@ cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStre
   if (S == 1) {
     LAUNCH(1)
   } else if (S == 3) {
+    LAUNCH(3)
+  } else {
+    LAUNCH(4)
+  }
+#undef LAUNCH
+  return cudaGetLastError();
+}
+
+// g: residual job on grid_res CTAs, gd: data-term job (S = 1) on grid_data CTAs; both use clusters of g.cluster CTAs
+cudaError_t pinn_generic_dual_launch(const GenParams& g_in, int S, int grid_res, const GenParams& gd_in, int grid_data,
+                                     cudaStream_t stream) {
+  GenParams g = g_in, gd = gd_in;
+  const size_t smem_res = pinn_generic_smem_bytes(g.net, S, &g.kch);
+  const size_t smem_data = pinn_generic_smem_bytes(gd.net, 1, &gd.kch);
+  const size_t smem = smem_res > smem_data ? smem_res : smem_data;
+  gd.cluster = g.cluster;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid_res + grid_data);
+  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+#define LAUNCH(SS)                                                                                                  \
+  e = cudaFuncSetAttribute(pinn_generic_dual_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+  if (e != cudaSuccess) return e;                                                                                   \
+  e = cudaLaunchKernelEx(&cfg, pinn_generic_dual_kernel<SS>, g, gd, grid_res);                                      \
+  if (e != cudaSuccess) return e;
+  if (S == 3) {
     LAUNCH(3)
   } else {
     LAUNCH(4)

@@ -25,6 +25,8 @@ struct GenParams {
   int64_t nf_global;
   int mode;
   const float* seed;    // S == 1: dL/du^ per point [N, n_out] (or null)
+  const float* u_data;  // S == 1: measurements [N, n_out]; the kernel forms data_c * (u^ - u)^2 and its adjoint (or null)
+  float data_c;         // data_weight / N_u
   const float* l1_sum;  // V3: device pointer to the job-wide sum |f| (or null)
   float* u_out;         // [N, n_out] or null
   float* f_out;         // [N, n_res] or null
@@ -40,6 +42,8 @@ struct GenParams {
 
 size_t pinn_generic_smem_bytes(const NetDesc& net, int S, int* kch_out);
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream);
+cudaError_t pinn_generic_dual_launch(const GenParams& g, int S, int grid_res, const GenParams& gd, int grid_data,
+                                     cudaStream_t stream);
 
 // small kernels (pinn_aux.cu)
 cudaError_t pinn_repack_launch(const NetDesc& net, const float* theta, float* wp, float* wt, cudaStream_t stream);

@@ -104,6 +104,16 @@ static ScratchDesc make_scratch_desc(const NetDesc& net, int S) {
     sd.zb[k] = off;
     off += S * net.npmax * PINN_TILE;
   }
+  sd.in0T = off;
+  off += S * PINN_TILE * 8;
+  for (int hl = 0; hl < net.L - 1; ++hl) {
+    sd.hidT[hl] = off;
+    off += S * PINN_TILE * net.np[hl + 1];
+  }
+  for (int k = 0; k < 2; ++k) {
+    sd.zbT[k] = off;
+    off += S * PINN_TILE * net.npmax;
+  }
   sd.total = off;
   return sd;
 }
@@ -183,7 +193,7 @@ static void fill_gen_params(const pinn_handle_s* h, int S, int mode, int loss, c
   g.rvlen = h->rvlen;
 }
 
-// one launch of the generic kernel; returns the grid used through *grid_out.  u_data != null (S == 1): the squared
+// one launch of the generic kernel; returns the number of partial-sum rows (= clusters) through *grid_out.  u_data != null (S == 1): the squared
 // data misfit and its adjoint are formed inside the kernel
 static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* X, int64_t n, const float* seed,
                        float* u_out, float* f_out, int admm_op, bool use_state, float* part, int* grid_out,
@@ -199,7 +209,7 @@ static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* 
   const int grid = gen_grid_for(h, n, &g.cluster);
   CK(pinn_generic_launch(g, S, grid, h->stream));
   h->launches += 1;
-  if (grid_out) *grid_out = grid;
+  if (grid_out) *grid_out = grid / g.cluster;
   return PINN_OK;
 }
 
@@ -212,18 +222,19 @@ static int run_generic_dual(pinn_handle_t h, int loss, int admm_op, bool use_sta
   fill_gen_params(h, h->S_res, GEN_MODE_TRAIN, loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, use_state, h->d_part, g);
   const int grid_res = gen_grid_for(h, h->n_f, &g.cluster);
   const int cs = g.cluster;
-  int64_t dtiles = (h->n_u + PINN_TILE - 1) / PINN_TILE;
-  if (dtiles > h->gen_grid_max / cs) dtiles = h->gen_grid_max / cs;
-  const int grid_data = (int)dtiles * cs;
+  // data clusters: one per tile (when the residual job leaves too few free CTA slots the last ones simply queue)
+  int64_t dclusters = (h->n_u + PINN_TILE - 1) / PINN_TILE;
+  if (dclusters > h->gen_grid_max / cs) dclusters = h->gen_grid_max / cs;
+  const int grid_data = (int)dclusters * cs;
   fill_gen_params(h, 1, GEN_MODE_TRAIN, PINN_LOSS_V4_MSE, h->d_Xu, h->n_u, nullptr, nullptr, nullptr, 0, false,
-                  h->d_part + (size_t)grid_res * h->rvlen, gd);
+                  h->d_part + (size_t)(grid_res / cs) * h->rvlen, gd);
   gd.u_data = h->d_u;
   gd.data_c = h->data_weight / (float)h->n_u;
   gd.cluster = cs;
   gd.scratch = h->d_scratch + (size_t)(grid_res / cs) * h->sd_res.total;
   CK(pinn_generic_dual_launch(g, h->S_res, grid_res, gd, grid_data, h->stream));
   h->launches += 1;
-  *rows_out = grid_res + grid_data;
+  *rows_out = (grid_res + grid_data) / cs;
   return PINN_OK;
 }
 

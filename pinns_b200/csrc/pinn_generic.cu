@@ -32,6 +32,22 @@ __device__ __forceinline__ void tile_sync(int cs) {
   }
 }
 
+#ifdef PINN_TRACE
+// debug builds (-DPINN_TRACE): CTA 0 thread 0 logs (tag, clock64) at phase boundaries; read back with pinn_debug_trace
+__device__ long long g_trace[2048];
+__device__ int g_trace_n;
+#define TRACE(tag)                                                              \
+  do {                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_trace_n < 1023) {                     \
+      g_trace[2 * g_trace_n] = (tag);                                           \
+      g_trace[2 * g_trace_n + 1] = clock64();                                   \
+      ++g_trace_n;                                                              \
+    }                                                                           \
+  } while (0)
+#else
+#define TRACE(tag)
+#endif
+
 template <int S>
 struct Streams {
   const float* p[S];
@@ -108,8 +124,11 @@ __device__ __forceinline__ void gemm_staged(const Streams<S>& in, int n_in, cons
         cp_async16(wsl + row * 8 + half * 4, wsrc + (size_t)row * ldw + half * 4);
       }
     }
+    TRACE(200);
     cp_async_wait_all();
+    TRACE(201);
     __syncthreads();
+    TRACE(202);
     if (active) {
 #pragma unroll 4
       for (int i = 0; i < kc; ++i) {
@@ -140,37 +159,70 @@ __device__ __forceinline__ void gemm_staged(const Streams<S>& in, int n_in, cons
     }
 }
 
-// W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
+// point-major ("transposed") copies of the weight-gradient operands: [stream][point][neuron], row stride ld.  The
+// producers (forward / reverse epilogues) write them next to the neuron-major blocks the GEMMs read, so staging a
+// weight-gradient operand is a plain 16-byte cp.async row copy instead of a transposing gather.
 template <int S>
-__device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const float* zb, int l, float* gp, float* smem,
-                            int crank, int cs, bool first) {
+struct StreamsT {
+  const float* p[S];
+  int ld;
+};
+
+template <int S>
+__device__ __forceinline__ StreamsT<S> layer_inputs_T(const GenParams& g, float* scr, int l) {
+  StreamsT<S> r;
+  if (l == 0) {
+    r.ld = 8;
+#pragma unroll
+    for (int s = 0; s < S; ++s) r.p[s] = scr + g.sd.in0T + s * T * 8;
+  } else {
+    r.ld = g.net.np[l];
+#pragma unroll
+    for (int s = 0; s < S; ++s) r.p[s] = scr + g.sd.hidT[l - 1] + s * T * r.ld;
+  }
+  return r;
+}
+
+// one stream's operands -> buf: Hs [T][np_in + 4] | Zs [T][np_out + 4]   (asynchronous)
+__device__ __forceinline__ void stage_wg(float* buf, const float* hsrc, int ld_h, int np_in, const float* zsrc, int ld_z,
+                                         int np_out) {
+  const int ldh = np_in + 4, ldz = np_out + 4;
+  float* Hs = buf;
+  float* Zs = buf + T * ldh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int p = warp; p < T; p += nwarps) {
+    for (int c = lane; c < np_in / 4; c += 32) cp_async16(Hs + p * ldh + c * 4, hsrc + (size_t)p * ld_h + c * 4);
+    for (int c = lane; c < np_out / 4; c += 32) cp_async16(Zs + p * ldz + c * 4, zsrc + (size_t)p * ld_z + c * 4);
+  }
+}
+
+// W-bar_l += Hin^T Z-bar summed over the tile's points and all streams; b-bar_l += sum_p Z-bar_0.
+// The per-stream operand tiles are double buffered when shared memory allows (nbuf == 2): stream s+1 lands while the
+// 8x8 register tiles of stream s are accumulated.
+template <int S>
+__device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const float* zbT, int l, float* gp, float* smem,
+                            int nbuf, int crank, int cs, bool first) {
   const int n_in = g.net.n[l], n_out = g.net.n[l + 1];
   const int np_in = g.net.np[l], np_out = g.net.np[l + 1];
   const int ldh = np_in + 4, ldz = np_out + 4;
-  float* Hs = smem;
-  float* Zs = smem + T * ldh;
+  const int bufsz = T * (2 * g.net.npmax + 8);
+  const int ld_z = g.net.npmax;
   const int nti = np_in / 8, ntj = np_out / 8;
   float* gW = gp + g.net.w_off[l];
   float* gb = gp + g.net.b_off[l];
   const int ntasks = nti * ntj;
   const bool one_task = ntasks <= cs * (int)blockDim.x;  // then the 8x8 accumulator tile lives across the stream loop
   float2 acc[8][4];
+  __syncthreads();  // earlier users of the staging region are done
+  stage_wg(smem, hin.p[0], hin.ld, np_in, zbT, ld_z, np_out);
   for (int s = 0; s < S; ++s) {
-    __syncthreads();
-    // transposing 4-byte cp.async: every element of both operands is in flight at once (one L2 round trip per stream)
-    for (int idx = threadIdx.x; idx < np_in * T; idx += blockDim.x) {
-      const int i = idx / T, p = idx % T;
-      if (i < n_in) cp_async4(Hs + p * ldh + i, hin.p[s] + i * T + p);
-      else Hs[p * ldh + i] = 0.f;
-    }
-    const float* zsrc = zb + (size_t)s * g.net.npmax * T;
-    for (int idx = threadIdx.x; idx < np_out * T; idx += blockDim.x) {
-      const int j = idx / T, p = idx % T;
-      if (j < n_out) cp_async4(Zs + p * ldz + j, zsrc + j * T + p);
-      else Zs[p * ldz + j] = 0.f;
-    }
+    float* buf = smem + (nbuf == 2 ? (s & 1) * bufsz : 0);
+    const float* Hs = buf;
+    const float* Zs = buf + T * ldh;
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // stream s landed; every thread is past stream s-1, whose buffer may be refilled
+    if (nbuf == 2 && s + 1 < S)
+      stage_wg(smem + ((s + 1) & 1) * bufsz, hin.p[s + 1], hin.ld, np_in, zbT + (size_t)(s + 1) * T * ld_z, ld_z, np_out);
     for (int task = crank * blockDim.x + threadIdx.x; task < ntasks; task += cs * blockDim.x) {
       const int ig = task / ntj, jg = task % ntj;
       if (!one_task || s == 0) {
@@ -218,6 +270,10 @@ __device__ void weight_grad(const GenParams& g, const Streams<S>& hin, const flo
         for (int p = 0; p < T; ++p) sum += Zs[p * ldz + j];
         gb[j] = first ? sum : gb[j] + sum;
       }
+    }
+    if (nbuf == 1 && s + 1 < S) {
+      __syncthreads();
+      stage_wg(smem, hin.p[s + 1], hin.ld, np_in, zbT + (size_t)(s + 1) * T * ld_z, ld_z, np_out);
     }
   }
   __syncthreads();
@@ -284,7 +340,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
   const int cs = g.cluster;                       // CTAs per tile
   const int crank = bid % cs, cid = bid / cs, nclusters = nblk / cs;
   float* scr = g.scratch + (size_t)cid * g.sd.total;
-  float* gp = g.part + (size_t)bid * g.rvlen;
+  float* gp = g.part + (size_t)cid * g.rvlen;  // one partial row per cluster: its CTAs own disjoint entries
   const bool backward = (g.mode != GEN_MODE_FORWARD);
   const int L = net.L;
   // shared memory: act [S][kch][32] (GEMM inputs) | { per-warp weight slices [nwarps][kch][8]  or  the weight-gradient
@@ -295,7 +351,14 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
   float* wsl = gst + warp * kch * 8;
   const int per_round = cs * nwarps;
 
-  for (int k = threadIdx.x; k < g.rvlen; k += blockDim.x) gp[k] = 0.f;
+  // a training pass overwrites every weight / bias entry on the CTA's first tile (plain stores in weight_grad), so
+  // only the lambda gradients and the sums need a zero; a forward-only pass leaves the gradient part defined as zero
+  if (backward) {
+    if (crank == 0)
+      for (int k = net.P + threadIdx.x; k < g.rvlen; k += blockDim.x) gp[k] = 0.f;
+  } else {
+    for (int k = crank * blockDim.x + threadIdx.x; k < g.rvlen; k += cs * blockDim.x) gp[k] = 0.f;
+  }
   float cB = g.lc.cB;
   if (g.lc.loss == PINN_LOSS_V3_L1SQ && g.l1_sum != nullptr) cB = 2.0f * g.lc.inv_nf * g.l1_sum[0];
   const float lam1 = g.theta[net.P], lam2 = g.theta[net.P + 1];
@@ -331,8 +394,25 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
         in0[(3 * 8 + 0) * T + lane] = 0.f;
         in0[(3 * 8 + 1) * T + lane] = 0.f;
       }
+      if (backward) {  // point-major copy for the layer-0 weight gradient
+        float4* in0T = reinterpret_cast<float4*>(scr + g.sd.in0T);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        in0T[(0 * T + lane) * 2] = make_float4(in0[0 * T + lane], in0[1 * T + lane], 0.f, 0.f);
+        in0T[(0 * T + lane) * 2 + 1] = zero4;
+        if (S >= 3) {
+          in0T[(1 * T + lane) * 2] = make_float4(2.0f / net.spanx, 0.f, 0.f, 0.f);
+          in0T[(1 * T + lane) * 2 + 1] = zero4;
+          in0T[(2 * T + lane) * 2] = make_float4(0.f, 2.0f / net.spant, 0.f, 0.f);
+          in0T[(2 * T + lane) * 2 + 1] = zero4;
+        }
+        if (S == 4) {
+          in0T[(3 * T + lane) * 2] = zero4;
+          in0T[(3 * T + lane) * 2 + 1] = zero4;
+        }
+      }
     }
     tile_sync(cs);
+    TRACE(1);
 
     // ---- forward ----
     for (int l = 0; l < L; ++l) {
@@ -346,10 +426,13 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
         const int jg = (r * cs + crank) * nwarps + warp;
         const bool active = jg < ngroups;
         float acc[S][8];
+        TRACE(100 + l);
         gemm_staged<S>(in, n_in, W, np_out, jg, active, r > 0, act, wsl, kch, lane, acc);
+        TRACE(120 + l);
         if (!active) continue;
         if (!head) {
           float* blk = scr + g.sd.hid[l];
+          float hT[S][8];  // the layer's output streams a, H_x, H_t, H_xx of this point
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             const int j = jg * 8 + jj;
@@ -357,17 +440,27 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
             const float a = pinn_tanh(z);
             const float d1 = fmaf(-a, a, 1.0f);
             blk[j * T + lane] = a;
+            hT[0][jj] = a;
             if (S >= 3) {
               const float zx = acc[1][jj], zt = acc[2][jj];
               blk[(1 * np_out + j) * T + lane] = zx;
               blk[(2 * np_out + j) * T + lane] = zt;
-              blk[((S - 1 + 1) * np_out + j) * T + lane] = d1 * zx;
-              blk[((S - 1 + 2) * np_out + j) * T + lane] = d1 * zt;
+              blk[((S - 1 + 1) * np_out + j) * T + lane] = hT[1][jj] = d1 * zx;
+              blk[((S - 1 + 2) * np_out + j) * T + lane] = hT[2][jj] = d1 * zt;
               if (S == 4) {
                 const float zxx = acc[3][jj];
                 blk[(3 * np_out + j) * T + lane] = zxx;
-                blk[((S - 1 + 3) * np_out + j) * T + lane] = d1 * fmaf(-2.0f * a, zx * zx, zxx);
+                blk[((S - 1 + 3) * np_out + j) * T + lane] = hT[3][jj] = d1 * fmaf(-2.0f * a, zx * zx, zxx);
               }
+            }
+          }
+          if (backward) {
+            float* hidT = scr + g.sd.hidT[l];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              float4* dst = reinterpret_cast<float4*>(hidT + ((size_t)s * T + lane) * np_out + jg * 8);
+              dst[0] = make_float4(hT[s][0], hT[s][1], hT[s][2], hT[s][3]);
+              dst[1] = make_float4(hT[s][4], hT[s][5], hT[s][6], hT[s][7]);
             }
           }
         } else {
@@ -381,7 +474,9 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
           }
         }
       }
+      TRACE(140 + l);
       tile_sync(cs);
+      TRACE(10 + l);
     }
 
     // ---- residual, loss terms, ADMM, adjoint seeds of the head outputs ----
@@ -389,6 +484,8 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
     if (warp == 0 && crank == 0) {
       const float* Y = scr + g.sd.Y;
       float* zb = scr + g.sd.zb[0];
+      float* zbT = scr + g.sd.zbT[0];  // [s][point][npmax]
+      const int ldT = net.npmax;
       const int ldz = net.npmax * T;
       if (S == 1) {  // data term: adjoints supplied by the caller (appendix A.3, dL/du^)
         for (int o = 0; o < 8; ++o) {
@@ -403,6 +500,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
             }
           }
           zb[o * T + lane] = sd;
+          zbT[(size_t)lane * ldT + o] = sd;
         }
       } else if (net.pde == PINN_PDE_BURGERS) {
         const float u = Y[lane], ux = Y[(1 * 8) * T + lane], ut = Y[(2 * 8) * T + lane];
@@ -418,10 +516,18 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
         ps.dl2 -= fbar * uxx;
         for (int o = 0; o < 8; ++o) {
           const bool o0 = (o == 0);
-          zb[0 * ldz + o * T + lane] = o0 ? fbar * lam1 * ux : 0.f;
-          zb[1 * ldz + o * T + lane] = o0 ? fbar * lam1 * u : 0.f;
-          zb[2 * ldz + o * T + lane] = o0 ? fbar : 0.f;
-          if (S == 4) zb[3 * ldz + o * T + lane] = o0 ? -lam2 * fbar : 0.f;
+          const float v0 = o0 ? fbar * lam1 * ux : 0.f, v1 = o0 ? fbar * lam1 * u : 0.f, v2 = o0 ? fbar : 0.f;
+          const float v3 = o0 ? -lam2 * fbar : 0.f;
+          zb[0 * ldz + o * T + lane] = v0;
+          zb[1 * ldz + o * T + lane] = v1;
+          zb[2 * ldz + o * T + lane] = v2;
+          zbT[((size_t)0 * T + lane) * ldT + o] = v0;
+          zbT[((size_t)1 * T + lane) * ldT + o] = v1;
+          zbT[((size_t)2 * T + lane) * ldT + o] = v2;
+          if (S == 4) {
+            zb[3 * ldz + o * T + lane] = v3;
+            zbT[((size_t)3 * T + lane) * ldT + o] = v3;
+          }
         }
       } else {  // Euler, outputs (rho,u,E), EUL:176-198 by the product rule
         const float k = 0.4f;
@@ -467,27 +573,34 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
         yb[2][1] = b2 * r;
         yb[2][2] = b3;
         for (int s = 0; s < 3; ++s)
-          for (int o = 0; o < 8; ++o) zb[s * ldz + o * T + lane] = (o < 3) ? yb[s][o] : 0.f;
+          for (int o = 0; o < 8; ++o) {
+            const float v = (o < 3) ? yb[s][o] : 0.f;
+            zb[s * ldz + o * T + lane] = v;
+            zbT[((size_t)s * T + lane) * ldT + o] = v;
+          }
       }
     }
     tile_sync(cs);
+    TRACE(30);
     if (!backward) continue;
 
     // ---- reverse sweep ----
     for (int l = L - 1; l >= 0; --l) {
       const float* zb = scr + g.sd.zb[cur];
-      const Streams<S> hin = layer_inputs<S>(g, scr, l);
+      const StreamsT<S> hinT = layer_inputs_T<S>(g, scr, l);
       Streams<S> zin;
 #pragma unroll
       for (int s = 0; s < S; ++s) zin.p[s] = zb + (size_t)s * net.npmax * T;
       const bool prestage = (l > 0) && (net.n[l + 1] <= kch);
       if (prestage) stage_act<S>(zin, 0, net.n[l + 1], act, kch);  // lands while the weight gradient runs
-      weight_grad<S>(g, hin, zb, l, gp, gst, crank, cs, first);
+      weight_grad<S>(g, hinT, scr + g.sd.zbT[cur], l, gp, gst, g.wg_nbuf, crank, cs, first);
+      TRACE(40 + l);
       if (l > 0) {
         const int n_j = net.n[l + 1], np_i = net.np[l];
         const float* WT = g.wt + net.wt_off[l];
         const float* blk = scr + g.sd.hid[l - 1];
         float* zn = scr + g.sd.zb[cur ^ 1];
+        float* znT = scr + g.sd.zbT[cur ^ 1];
         const int ldz = net.npmax * T;
         const int ngroups = np_i / 8;
         for (int r = 0; r * per_round < ngroups; ++r) {
@@ -496,6 +609,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
           float acc[S][8];
           gemm_staged<S>(zin, n_j, WT, np_i, ig, active, prestage || r > 0, act, wsl, kch, lane, acc);
           if (!active) continue;
+          float zT[S][8];  // this point's new adjoints, for the point-major copy
 #pragma unroll
           for (int ii = 0; ii < 8; ++ii) {
             const int i = ig * 8 + ii;
@@ -503,7 +617,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
             const float d1 = fmaf(-a, a, 1.0f);
             const float hb = acc[0][ii];
             if (S == 1) {
-              zn[i * T + lane] = d1 * hb;
+              zn[i * T + lane] = zT[0][ii] = d1 * hb;
             } else {
               const float d2 = -2.0f * a * d1;
               const float zx = blk[(1 * np_i + i) * T + lane], zt = blk[(2 * np_i + i) * T + lane];
@@ -517,15 +631,22 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
                 const float d3 = -2.0f * d1 * fmaf(-3.0f * a, a, 1.0f);
                 zbar += d2 * zxx * hxxb + d3 * zx * zx * hxxb;
                 zxbar += 2.0f * d2 * zx * hxxb;
-                zn[3 * ldz + i * T + lane] = d1 * hxxb;
+                zn[3 * ldz + i * T + lane] = zT[S - 1][ii] = d1 * hxxb;
               }
-              zn[0 * ldz + i * T + lane] = zbar;
-              zn[1 * ldz + i * T + lane] = zxbar;
-              zn[2 * ldz + i * T + lane] = ztbar;
+              zn[0 * ldz + i * T + lane] = zT[0][ii] = zbar;
+              zn[1 * ldz + i * T + lane] = zT[S > 1 ? 1 : 0][ii] = zxbar;
+              zn[2 * ldz + i * T + lane] = zT[S > 2 ? 2 : 0][ii] = ztbar;
             }
+          }
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float4* dst = reinterpret_cast<float4*>(znT + ((size_t)s * T + lane) * net.npmax + ig * 8);
+            dst[0] = make_float4(zT[s][0], zT[s][1], zT[s][2], zT[s][3]);
+            dst[1] = make_float4(zT[s][4], zT[s][5], zT[s][6], zT[s][7]);
           }
         }
         tile_sync(cs);
+        TRACE(60 + l);
         cur ^= 1;
       }
     }
@@ -533,8 +654,11 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
     first = false;
   }
 
-  // ---- per-CTA partial sums ----
-  if (warp == 0) {
+  if (first && backward) {  // no tile reached this CTA (the host never sizes a grid that way): keep the row defined
+    for (int k = crank * blockDim.x + threadIdx.x; k < net.P; k += cs * blockDim.x) gp[k] = 0.f;
+  }
+  // ---- per-cluster partial sums (the residual / data bookkeeping is done by rank 0's first warp) ----
+  if (warp == 0 && crank == 0) {
 #pragma unroll
     for (int k = 0; k < PINN_NSUMS; ++k) {
       const float v = warp_sum(ps.v[k]);
@@ -566,24 +690,40 @@ __global__ void __launch_bounds__(GEN_THREADS, 2)
 
 }  // namespace
 
-// shared memory of one CTA and the K chunk it allows: act [S][kch][T] + max(weight slices [warps][kch][8], weight-gradient
-// staging [T][2 npmax + 8]); kch covers the widest layer unless that would pass ~216 KB
-size_t pinn_generic_smem_bytes(const NetDesc& net, int S, int* kch_out) {
+#ifdef PINN_TRACE
+extern "C" int pinn_debug_trace(long long* out, int* n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(n, g_trace_n, sizeof(int));
+  cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 2048);
+  int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int));
+  return 0;
+}
+#endif
+
+// shared memory of one CTA: act [S][kch][T] + max(weight slices [warps][kch][8], nbuf weight-gradient staging buffers
+// [T][2 npmax + 8]).  kch covers the widest layer unless that would pass ~216 KB; the staging is double buffered when it
+// fits and (small grids) occupancy is not at stake
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out) {
   const size_t gsz = (size_t)T * (2 * net.npmax + 8);
   const size_t budget = 216 * 1024 / sizeof(float);
   int kch = net.npmax;
-  auto total = [&](int k) {
+  auto total = [&](int k, int nbuf) {
     const size_t w = (size_t)(GEN_THREADS / 32) * k * 8;
-    return (size_t)S * k * T + (w > gsz ? w : gsz);
+    return (size_t)S * k * T + (w > nbuf * gsz ? w : nbuf * gsz);
   };
-  while (kch > 8 && total(kch) > budget) kch -= 8;
+  while (kch > 8 && total(kch, 1) > budget) kch -= 8;
+  int nbuf = 1;
+  const size_t half = 113 * 1024 / sizeof(float);  // two CTAs per SM below this
+  if (kch == net.npmax && total(kch, 2) <= budget && !(want_occupancy && total(kch, 1) <= half && total(kch, 2) > half)) nbuf = 2;
   if (kch_out) *kch_out = kch;
-  return total(kch) * sizeof(float);
+  if (nbuf_out) *nbuf_out = nbuf;
+  return total(kch, nbuf) * sizeof(float);
 }
 
 cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStream_t stream) {
   GenParams g = g_in;
-  const size_t smem = pinn_generic_smem_bytes(g.net, S, &g.kch);
+  const size_t smem = pinn_generic_smem_bytes(g.net, S, grid > 148, &g.kch, &g.wg_nbuf);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -618,8 +758,8 @@ cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStre
 cudaError_t pinn_generic_dual_launch(const GenParams& g_in, int S, int grid_res, const GenParams& gd_in, int grid_data,
                                      cudaStream_t stream) {
   GenParams g = g_in, gd = gd_in;
-  const size_t smem_res = pinn_generic_smem_bytes(g.net, S, &g.kch);
-  const size_t smem_data = pinn_generic_smem_bytes(gd.net, 1, &gd.kch);
+  const size_t smem_res = pinn_generic_smem_bytes(g.net, S, grid_res + grid_data > 148, &g.kch, &g.wg_nbuf);
+  const size_t smem_data = pinn_generic_smem_bytes(gd.net, 1, true, &gd.kch, &gd.wg_nbuf);
   const size_t smem = smem_res > smem_data ? smem_res : smem_data;
   gd.cluster = g.cluster;
   cudaLaunchConfig_t cfg;

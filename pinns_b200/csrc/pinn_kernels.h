@@ -10,6 +10,10 @@ struct ScratchDesc {
   int hid[PINN_MAX_LAYERS];   // per hidden layer: (2S-1) x np x T   a | Z_x Z_t Z_xx | H_x H_t H_xx
   int Y;                      // S x 8 x T  head outputs per stream
   int zb[2];                  // S x npmax x T  adjoint ping-pong
+  // point-major copies ([stream][point][neuron]) of the weight-gradient operands
+  int in0T;                   // S x T x 8
+  int hidT[PINN_MAX_LAYERS];  // per hidden layer: S x T x np   a | H_x H_t H_xx
+  int zbT[2];                 // S x T x npmax
   int total;                  // floats per CTA
 };
 
@@ -38,9 +42,10 @@ struct GenParams {
   int rvlen;
   int cluster;          // CTAs per 32-point tile (1, 2, 4 or 8); grid = clusters * cluster
   int kch;              // K rows staged per shared-memory chunk (set by pinn_generic_launch)
+  int wg_nbuf;          // weight-gradient staging buffers (1 or 2; set by pinn_generic_launch)
 };
 
-size_t pinn_generic_smem_bytes(const NetDesc& net, int S, int* kch_out);
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out);
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream);
 cudaError_t pinn_generic_dual_launch(const GenParams& g, int S, int grid_res, const GenParams& gd, int grid_data,
                                      cudaStream_t stream);

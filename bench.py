@@ -12,8 +12,9 @@ from the job-wide Philox stream (seed 1234), N_f = 16*2^20 points PER GPU (weak 
 134 MB of inputs per GPU exceed the 126 MB L2, so no flush is needed between iterations).
 
 `value`  : whole-job points/s, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : the same metric through the public class API with HOST buffers: each step copies the
-           step's collocation points from pinned host memory and reads the loss back.
+`e2e`    : the same metric through the public class API with HOST buffers: each step feeds the
+           step's collocation points from pinned host memory (pinn_feed_collocation: chunked H2D on a
+           copy stream, the kernel starts on chunk k while chunk k+1 is on the bus) and reads the loss back.
 `roofline`: FP32-FMA bound (>= 5700 FLOP/B, compute bound): algorithmic
            FLOPs (68 320 per point) / measured duration of the fused kernel, against an FFMA-only
            micro-kernel measured on this GPU in this run (MEASURED_PEAKS.json has no fp32 entry).
@@ -278,7 +279,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nf * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "api": "PhysicsInformedNN.train_step_from_host(pinned X_f): H2D + loss/grad(+allreduce) + Adam + loss D2H"},
+                "api": "PhysicsInformedNN.train_step_from_host(pinned X_f): chunked H2D feed overlapped with the kernel + loss/grad(+allreduce) + Adam + loss D2H"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -108,6 +108,12 @@ int pinn_get_lambda(pinn_handle_t h, float* lambda1, float* lambda2);
  * (sum over ranks) used in the 1/N_f factors; pass 0 for "same as n_f".              */
 int pinn_set_data(pinn_handle_t h, const float* X_u, const float* u, int64_t n_u, int on_device);
 int pinn_set_collocation(pinn_handle_t h, const float* X_f, int64_t n_f, int64_t nf_global, int on_device);
+/* the per-step feed of the training loop, `sess.run(train_op_Adam, feed_dict={x_f, t_f, ...})` (INF-L2:127-135,
+ * AB-ADMM:220-228): X_f_host is HOST memory (pinned for a truly asynchronous copy) that must stay untouched
+ * until the next synchronising call.  Returns at once; the points travel in growing chunks on a copy stream
+ * and the next pinn_loss_grad_device / pinn_adam_steps starts on chunk k while chunk k+1 is still on the
+ * bus (fused path; the other paths and the forward-only passes wait for the whole batch).              */
+int pinn_feed_collocation(pinn_handle_t h, const float* X_f_host, int64_t n_f, int64_t nf_global);
 /* device-side replacement of np.random.uniform(lb, ub, [N_f,1]) x2 (AB-ADMM:220-221, EUL:232-233):
  * counter-based Philox4x32-10, point i of the job uses counter (first_index + i), so the
  * stream is independent of how the job is sharded over GPUs.                            */

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "pinn_get_lambda": (C.c_int, [_H, _fp, _fp]),
     "pinn_set_data": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "pinn_set_collocation": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
+    "pinn_feed_collocation": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64]),
     "pinn_sample_collocation": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "pinn_get_collocation": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "pinn_set_data_weight": (C.c_int, [_H, C.c_float]),

@@ -65,6 +65,14 @@ struct pinn_handle_s {
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // pairs (before, after) of the dominant kernel
   size_t ev_used = 0;
+
+  // host feed in flight (pinn_feed_collocation): chunk c = points [feed_first[c], feed_first[c+1]) has landed in
+  // d_Xf_owned once feed_ev[c] fires on copy_stream
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t feed_start = nullptr;
+  std::vector<cudaEvent_t> feed_ev;
+  std::vector<int64_t> feed_first;
+  int feed_chunks = 0;
 };
 
 static std::string g_create_err;
@@ -400,6 +408,12 @@ int pinn_destroy(pinn_handle_t h) {
   fused_destroy(h->fused);
   tensor_destroy(h->tensor);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamDestroy(h->copy_stream);
+    cudaEventDestroy(h->feed_start);
+  }
+  for (cudaEvent_t e : h->feed_ev) cudaEventDestroy(e);
   float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
                    h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
                    h->d_l1sum, h->d_data_loss};
@@ -503,6 +517,8 @@ int pinn_set_data(pinn_handle_t h, const float* X_u, const float* u, int64_t n_u
   return PINN_OK;
 }
 
+static int feed_join(pinn_handle_t h);
+
 static int ensure_xf_owned(pinn_handle_t h, int64_t n_f) {
   if (n_f > h->xf_cap) {
     if (h->d_Xf_owned) cudaFree(h->d_Xf_owned);
@@ -516,6 +532,10 @@ static int ensure_xf_owned(pinn_handle_t h, int64_t n_f) {
 int pinn_set_collocation(pinn_handle_t h, const float* X_f, int64_t n_f, int64_t nf_global, int on_device) {
   if (!h || !X_f || n_f <= 0) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));
+  {
+    int rc = feed_join(h);
+    if (rc) return rc;
+  }
   if (on_device) {
     h->d_Xf = const_cast<float*>(X_f);  // borrowed
   } else {
@@ -530,10 +550,73 @@ int pinn_set_collocation(pinn_handle_t h, const float* X_f, int64_t n_f, int64_t
   return PINN_OK;
 }
 
+// chunk boundaries of a host feed: a small first chunk (its copy is the only one nobody hides), then 4x growth in
+// whole rounds of the persistent grid.  The kernel consumes ~4.4 GB/s of points, PCIe delivers 25-55 GB/s, so the
+// copy of chunk k+1 is done before the kernel has finished chunk k as long as the growth factor stays below that ratio.
+static void feed_plan(const pinn_handle_s* h, int64_t n_f, std::vector<int64_t>& first) {
+  first.clear();
+  first.push_back(0);
+  const int64_t round = (int64_t)h->fused.grid * (h->fused.threads / 32) * 32;  // points per round of all warps
+  const bool chunked = h->fused.enabled && h->cfg.loss != PINN_LOSS_V3_L1SQ && round > 0 && n_f >= 16 * round;
+  if (chunked) {
+    int64_t at = 0, len = 4 * round;
+    while (at + len < n_f) {
+      at += len;
+      first.push_back(at);
+      len *= 4;
+    }
+  }
+  first.push_back(n_f);
+}
+
+int pinn_feed_collocation(pinn_handle_t h, const float* X_f_host, int64_t n_f, int64_t nf_global) {
+  if (!h || !X_f_host || n_f <= 0) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_xf_owned(h, n_f);
+  if (rc) return rc;
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->feed_start, cudaEventDisableTiming));
+  }
+  feed_plan(h, n_f, h->feed_first);
+  const int nc = (int)h->feed_first.size() - 1;
+  while ((int)h->feed_ev.size() < nc) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->feed_ev.push_back(e);
+  }
+  // the previous step's kernels may still be reading the buffer
+  CK(cudaEventRecord(h->feed_start, h->stream));
+  CK(cudaStreamWaitEvent(h->copy_stream, h->feed_start, 0));
+  for (int c = 0; c < nc; ++c) {
+    const int64_t a = h->feed_first[c], b = h->feed_first[c + 1];
+    CK(cudaMemcpyAsync(h->d_Xf_owned + 2 * a, X_f_host + 2 * a, (size_t)(b - a) * 2 * sizeof(float), cudaMemcpyHostToDevice,
+                       h->copy_stream));
+    CK(cudaEventRecord(h->feed_ev[c], h->copy_stream));
+  }
+  h->feed_chunks = nc;
+  h->d_Xf = h->d_Xf_owned;
+  h->n_f = n_f;
+  h->nf_global = nf_global > 0 ? nf_global : n_f;
+  h->l1_ready = false;
+  return PINN_OK;
+}
+
+// everything that is not the chunk-aware fused training pass waits for the whole feed
+static int feed_join(pinn_handle_t h) {
+  if (h->feed_chunks > 0) {
+    CK(cudaStreamWaitEvent(h->stream, h->feed_ev[h->feed_chunks - 1], 0));
+    h->feed_chunks = 0;
+  }
+  return PINN_OK;
+}
+
 int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index, int64_t n_f, int64_t nf_global) {
   if (!h || n_f <= 0) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));
-  int rc = ensure_xf_owned(h, n_f);
+  int rc = feed_join(h);
+  if (rc) return rc;
+  rc = ensure_xf_owned(h, n_f);
   if (rc) return rc;
   CK(pinn_sample_launch(h->d_Xf_owned, n_f, seed, first_index, h->net.lbx, h->net.lbt, h->net.spanx, h->net.spant,
                         h->stream));
@@ -548,6 +631,10 @@ int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index
 int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device) {
   if (!h || !X_f) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_get_collocation: no collocation points set");
+  {
+    int rc = feed_join(h);
+    if (rc) return rc;
+  }
   CK(cudaMemcpyAsync(X_f, h->d_Xf, (size_t)h->n_f * 2 * sizeof(float),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
   if (!on_device) CK(cudaStreamSynchronize(h->stream));
@@ -647,17 +734,42 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
       ad.beta2 = h->beta2;
       ad.eps = h->eps;
     }
-    rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f,
-                   h->nf_global > 0 ? h->nf_global : h->n_f, mode,
-                   (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr,
-                   state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr,
-                   with_data ? h->d_Xu : nullptr, with_data ? h->d_u : nullptr, h->n_u,
-                   with_data ? h->data_weight / (float)h->n_u : 0.f, h->d_packed, ad, e0, e1, h->stream, h->err);
+    const int64_t nfg = h->nf_global > 0 ? h->nf_global : h->n_f;
+    const float* l1 = (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr;
+    const float data_c = with_data ? h->data_weight / (float)h->n_u : 0.f;
+    if (h->feed_chunks > 1 && mode == GEN_MODE_TRAIN && admm_op == 0) {
+      // host-fed batch: one launch per chunk as soon as its copy has landed, accumulators carried over, the data
+      // term rides with the last chunk, one reduction (+ Adam) at the end
+      const int nc = h->feed_chunks;
+      h->feed_chunks = 0;
+      for (int c = 0; c < nc && rc == PINN_OK; ++c) {
+        const int64_t a = h->feed_first[c], n = h->feed_first[c + 1] - a;
+        const bool last = (c == nc - 1);
+        CK(cudaStreamWaitEvent(h->stream, h->feed_ev[c], 0));
+        rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf + 2 * a, n, nfg, mode, l1,
+                       state ? h->d_z + a : nullptr, state ? h->d_gamma + a : nullptr, 0, nullptr, nullptr,
+                       (with_data && last) ? h->d_Xu : nullptr, (with_data && last) ? h->d_u : nullptr, h->n_u, data_c,
+                       last ? h->d_packed : nullptr, ad, c == 0 ? e0 : nullptr, last ? e1 : nullptr, h->stream, h->err,
+                       /*accumulate=*/c > 0, /*grid_fixed=*/h->fused.grid);
+        h->launches += 1;
+      }
+      if (rc) return rc;
+      h->launches -= 1;  // the common tail below counts the last kernel + the reduction
+    } else {
+      rc = feed_join(h);
+      if (rc) return rc;
+      rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f, nfg, mode, l1,
+                     state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr,
+                     with_data ? h->d_Xu : nullptr, with_data ? h->d_u : nullptr, h->n_u, data_c, h->d_packed, ad, e0, e1,
+                     h->stream, h->err);
+    }
     if (rc) return rc;
     h->launches += 2;
     if (fuse_adam) h->weights_dirty = h->tensor_dirty = true;
     return PINN_OK;
   }
+  rc = feed_join(h);
+  if (rc) return rc;
   int grid = 0;
   if (h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS)) {
     if (h->tensor_dirty) {

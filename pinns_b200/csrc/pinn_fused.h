@@ -31,7 +31,11 @@ void fused_destroy(FusedState& fs);
 // residual term on the collocation points (+ the squared data term on Xu/ud as extra batches when Xu != null):
 // loss sums (+ gradient in mode TRAIN) -> packed (overwritten); optional fused Adam update of theta.
 // ev_before / ev_after (optional) bracket the main kernel only.
+// accumulate = 1 adds to the warp-private accumulators of the previous launch instead of zeroing them and
+// packed = null skips the reduction: a batch that arrives from the host in chunks is one launch per chunk
+// (grid_fixed > 0 pins the grid so that every chunk owns the same regions) and one reduction at the end.
 int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const float* theta, const float* X, int64_t n,
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
               float* f_out, const float* Xu, const float* ud, int64_t n_u, float data_c, float* packed, const AdamFused& ad,
-              cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream, std::string& err);
+              cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream, std::string& err, int accumulate = 0,
+              int grid_fixed = 0);

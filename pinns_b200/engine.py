@@ -170,6 +170,24 @@ class Engine:
                  "pinn_set_collocation")
         self.n_f = int(n_f)
 
+    def feed_collocation(self, X_f_host, nf_global: int = 0):
+        """The per-step feed_dict of the training loop (INF-L2:127-135): X_f_host is a float32 [N,2] HOST
+        tensor / array (pinned memory makes the copy asynchronous).  Returns at once; the next loss_grad_device /
+        adam_steps consumes the points chunk by chunk while the rest is still on the bus.  The caller keeps the
+        buffer untouched until the step's result has been read back."""
+        if _is_torch_tensor(X_f_host):
+            import torch
+            if X_f_host.is_cuda or X_f_host.dtype != torch.float32 or not X_f_host.is_contiguous():
+                raise ValueError("feed_collocation needs a contiguous float32 host tensor [N,2]")
+            ptr, n = X_f_host.data_ptr(), X_f_host.shape[0]
+        else:
+            if X_f_host.dtype != np.float32 or not X_f_host.flags["C_CONTIGUOUS"]:
+                raise ValueError("feed_collocation needs a C-contiguous float32 array [N,2]")
+            ptr, n = X_f_host.ctypes.data, X_f_host.shape[0]
+        self._keep = [X_f_host]
+        self._ck(capi.lib.pinn_feed_collocation(self._h, C.c_void_p(ptr), int(n), int(nf_global)), "pinn_feed_collocation")
+        self.n_f = int(n)
+
     def sample_collocation(self, seed: int, first_index: int, n_f: int, nf_global: int = 0):
         self._ck(capi.lib.pinn_sample_collocation(self._h, int(seed), int(first_index), int(n_f), int(nf_global)),
                  "pinn_sample_collocation")

@@ -101,15 +101,10 @@ class _Base:
         the step's residual loss.  Returns that loss term."""
         import torch
         eng = self.engine
-        dev = torch.device("cuda", eng.device)
-        n = X_f_host.shape[0]
-        buf = getattr(self, "_dev_xf", None)
-        if buf is None or buf.shape[0] != n:
-            buf = self._dev_xf = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        if getattr(self, "_loss_host", None) is None:
             self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
             self._packed = eng.packed_tensor()
-        buf.copy_(X_f_host, non_blocking=True)
-        eng.set_collocation(buf, nf_global)
+        eng.feed_collocation(X_f_host, nf_global)   # asynchronous, chunked: the kernel starts on the first chunk
         if stepper is not None:
             stepper.adam_step()
         else:

@@ -185,3 +185,37 @@ def test_v1_unsquared_data_norm_gradient_is_nan_at_zero_misfit_like_tf():
     eng.set_data(c["X_u"], u_self.astype(np.float64))
     loss, grad = eng.loss_grad()
     assert np.isfinite(loss) and np.isnan(grad).any()
+
+
+@pytest.mark.parametrize("loss", [tg.LOSS_V4, tg.LOSS_V5])
+@pytest.mark.parametrize("n_f", [1000, 148 * 8 * 32 * 16 + 77, (1 << 21) + 5])
+def test_host_feed_in_chunks_equals_resident_batch(loss, n_f):
+    """pinn_feed_collocation (the per-step feed_dict, INF-L2:127-135): the batch arrives from pinned host memory in
+    chunks and the fused kernel accumulates over one launch per chunk -- same loss and gradient as the resident batch
+    (only the summation order over warps differs), z/gamma offsets included, and a fed Adam step moves theta alike."""
+    import torch
+    c = make_case(tg.PDE_BURGERS, B20, loss, 100, 64, seed=21)
+    lb, ub = c["prob"].lb, c["prob"].ub
+    X = sample_collocation(5, 0, n_f, lb, ub)
+    rng = np.random.default_rng(3)
+    z = (0.3 * rng.standard_normal((n_f, 1))).astype(np.float32)
+    g = (0.3 * rng.standard_normal((n_f, 1))).astype(np.float32)
+    outs, thetas = [], []
+    for fed in (False, True):
+        eng = make_engine(c, trainable_lambda=True)
+        host = torch.from_numpy(X.copy()).pin_memory()
+        if fed:
+            eng.feed_collocation(host)
+        else:
+            eng.set_collocation(X)
+        if loss == tg.LOSS_V5:
+            eng.admm_set_state(z, g)
+        outs.append(eng.loss_grad())
+        if fed:
+            eng.feed_collocation(host)
+        eng.adam_steps(1)
+        thetas.append(eng.get_params())
+        assert np.array_equal(eng.get_collocation(), X)
+    assert abs(outs[0][0] - outs[1][0]) <= 2e-6 * abs(outs[0][0])
+    assert rel_err(outs[1][1], outs[0][1]) <= 5e-6
+    assert rel_err(thetas[1] - c["theta"], thetas[0] - c["theta"]) <= 1e-3   # Adam's first step is +-lr per parameter

@@ -133,8 +133,71 @@ def save_e2e(full=False, fp32=False):
     print("e2e", out)
 
 
+def trajectory_schedule(which):
+    """Fixed-batch Adam schedules shared by the oracle (here) and tests/test_models_gpu.py for BASELINE configs 2 and 3.
+    identification: burgers_shock, N_u = 2000 INTERIOR grid samples, N_f = 2000 uniform points,
+                    loss AB-L2:59-60, lambda trainable from (0, ID-L2b:90's 0.0031831), 1500 TF-1 Adam steps.
+    euler:          Abgrall_eulers, [2,200x5,3], N_data = 200 of the IC/BC points (EUL:316-326), N_f = 1000 uniform
+                    points, pen = 40, plain-MSE residual loss, 300 Adam steps.
+    The batch is held fixed (no per-epoch resampling) so that the trajectory is a deterministic function of the inputs."""
+    from oracle import data as odata
+    if which == "identification":
+        sol = dict(np.load(os.path.join(HERE, "data", "burgers_shock.npz")))
+        g = odata.burgers_identification_inputs(sol, N_u=100, N_f=2000, seed=1234)
+        rng = np.random.default_rng(1234)
+        idx = rng.choice(g["X_star"].shape[0], 2000, replace=False)
+        g.update(X_u=g["X_star"][idx, :], u=g["u_star"][idx, :])
+        layers = [2] + [20] * 8 + [1]
+        theta0 = tg.xavier_init(layers, np.random.default_rng(4321))
+        prob = tg.Problem(layers, g["lb"], g["ub"], pde=tg.PDE_BURGERS, loss=tg.LOSS_V4, lam1=0.0, lam2=0.0031831)
+        return g, layers, theta0, prob, dict(adam_steps=1500, record=[0, 10, 100, 500, 1000, 1500])
+    sol = dict(np.load(os.path.join(HERE, "data", "Abgrall_eulers.npz")))
+    g = odata.euler_inputs(sol, N_data=200, N_f=1000, seed=1234)
+    layers = [2] + [200] * 5 + [3]
+    theta0 = tg.xavier_init(layers, np.random.default_rng(4321))
+    prob = tg.Problem(layers, g["lb"], g["ub"], pde=tg.PDE_EULER, loss=tg.LOSS_EULER_MSE, rho=40.0)
+    return g, layers, theta0, prob, dict(adam_steps=300, record=[0, 10, 50, 100, 200, 300])
+
+
+def save_trajectory(which):
+    import torch
+    torch.set_num_threads(6)
+    g, layers, theta0, prob, sched = trajectory_schedule(which)
+    trainable = which == "identification"
+    theta = theta0.astype(np.float64)
+    lam = np.array([np.float32(prob.lam1), np.float32(prob.lam2)], np.float64)
+    opt = TF1Adam(theta.size + (2 if trainable else 0))
+    rec = {"steps": [], "loss": [], "lambda1": [], "lambda2": []}
+    for it in range(sched["adam_steps"] + 1):
+        pr = tg.Problem(layers, prob.lb, prob.ub, pde=prob.pde, loss=prob.loss, lam1=lam[0], lam2=lam[1], rho=prob.rho)
+        ev = tg.evaluate(theta, pr, g["X_u"], g["u"], g["X_f"])
+        if it in sched["record"]:
+            rec["steps"].append(it); rec["loss"].append(float(ev.loss)); rec["lambda1"].append(float(lam[0])); rec["lambda2"].append(float(lam[1]))
+        if it == sched["adam_steps"]:
+            break
+        if trainable:
+            new = opt.step(np.concatenate([theta, lam]), np.concatenate([ev.grad, ev.dlam]))
+            theta, lam = new[:-2], new[-2:]
+        else:
+            theta = opt.step(theta, ev.grad)
+    pr = tg.Problem(layers, prob.lb, prob.ub, pde=prob.pde, loss=prob.loss, lam1=lam[0], lam2=lam[1], rho=prob.rho)
+    pred, _ = tg.predict(theta, pr, g["X_star"])
+    if which == "identification":
+        rec["error_u"] = tg.relative_l2(g["u_star"], pred)
+    else:
+        rec["error_rho"] = tg.relative_l2(g["rho_star"], pred[:, 0:1])
+        rec["error_u"] = tg.relative_l2(g["u_star"], pred[:, 1:2])
+        rec["error_E"] = tg.relative_l2(g["E_star"], pred[:, 2:3])
+    json.dump(rec, open(os.path.join(HERE, "trajectory_%s.json" % which), "w"), indent=1)
+    print("trajectory", which, rec)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["data", "vectors"]
+    if "trajectory_identification" in what:
+        save_trajectory("identification")
+    if "trajectory_euler" in what:
+        save_trajectory("euler")
     if "data" in what:
         save_data()
     if "vectors" in what:

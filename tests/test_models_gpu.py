@@ -94,3 +94,40 @@ def test_full_config1_accuracy():
     u, _ = m.predict(g["X_star"])
     err = tg.relative_l2(g["u_star"], u)
     assert err <= max(1.10 * gold["error_u_final"], 5e-3), (err, res.fun, gold)
+
+
+@pytest.mark.parametrize("which", ["identification", "euler"])
+def test_fixed_batch_adam_trajectory_tracks_the_oracle(which):
+    """BASELINE configs 2 (Burgers identification, trainable lambda, N_u = 2000 interior samples) and 3 (Euler
+    [2,200x5,3], N_data = 200, N_f = 1000): the device-resident Adam loop on a fixed batch follows the fp64 oracle's
+    committed trajectory (tests/golden/trajectory_*.json): loss curve, lambda estimates and the grid errors at the end.
+    fp32 rounding is amplified along an Adam trajectory, hence the loose late-step tolerances (stated below)."""
+    from tests.golden.make_fixtures import trajectory_schedule
+    from pinns_b200 import Engine
+    gold = json.load(open(os.path.join(GOLD, "trajectory_%s.json" % which)))
+    g, layers, theta0, prob, sched = trajectory_schedule(which)
+    trainable = which == "identification"
+    eng = Engine(layers, prob.lb, prob.ub, pde=prob.pde, loss="v4", lambda1=prob.lam1, lambda2=prob.lam2, rho=prob.rho,
+                 trainable_lambda=trainable)
+    eng.set_params(theta0)
+    eng.set_data(g["X_u"], g["u"])
+    eng.set_collocation(g["X_f"])
+    done = 0
+    for k, step in enumerate(gold["steps"]):
+        eng.adam_steps(step - done)
+        done = step
+        loss = eng.loss_value()
+        tol = 1e-4 if step <= 10 else (2e-2 if step <= 100 else 0.15)   # relative, vs the fp64 trajectory
+        assert abs(loss - gold["loss"][k]) <= tol * gold["loss"][k], (step, loss, gold["loss"][k])
+        if trainable:
+            l1, l2 = eng.get_lambda()
+            ltol = 1e-5 if step <= 10 else (2e-3 if step <= 100 else 0.05)  # absolute on lambda1, scaled for lambda2
+            assert abs(l1 - gold["lambda1"][k]) <= ltol and abs(l2 - gold["lambda2"][k]) <= 0.1 * ltol, (step, l1, l2)
+    pred, _ = eng.predict(g["X_star"], want_f=False)
+    if trainable:
+        err = {"error_u": tg.relative_l2(g["u_star"], pred)}
+    else:
+        err = {"error_rho": tg.relative_l2(g["rho_star"], pred[:, 0:1]), "error_u": tg.relative_l2(g["u_star"], pred[:, 1:2]),
+               "error_E": tg.relative_l2(g["E_star"], pred[:, 2:3])}
+    for k, v in err.items():   # north_star: final relative L2 error within 10 % of the reference's
+        assert abs(v - gold[k]) <= 0.10 * gold[k], (k, v, gold[k])

@@ -101,7 +101,9 @@ def test_fixed_batch_adam_trajectory_tracks_the_oracle(which):
     """BASELINE configs 2 (Burgers identification, trainable lambda, N_u = 2000 interior samples) and 3 (Euler
     [2,200x5,3], N_data = 200, N_f = 1000): the device-resident Adam loop on a fixed batch follows the fp64 oracle's
     committed trajectory (tests/golden/trajectory_*.json): loss curve, lambda estimates and the grid errors at the end.
-    fp32 rounding is amplified along an Adam trajectory, hence the loose late-step tolerances (stated below)."""
+    fp32 rounding is amplified along an Adam trajectory and the loss itself becomes spiky once Adam's step is large
+    against the curvature (lr 1e-3), hence the loose late-step LOSS tolerances stated below; the lambda estimates and
+    the grid errors, which integrate over the trajectory, stay within 5e-3 / 10 %."""
     from tests.golden.make_fixtures import trajectory_schedule
     from pinns_b200 import Engine
     gold = json.load(open(os.path.join(GOLD, "trajectory_%s.json" % which)))
@@ -117,11 +119,11 @@ def test_fixed_batch_adam_trajectory_tracks_the_oracle(which):
         eng.adam_steps(step - done)
         done = step
         loss = eng.loss_value()
-        tol = 1e-4 if step <= 10 else (2e-2 if step <= 100 else 0.15)   # relative, vs the fp64 trajectory
+        tol = 1e-4 if step <= 10 else (2e-2 if step <= 100 else (0.15 if step <= 500 else 0.4))   # relative, vs fp64
         assert abs(loss - gold["loss"][k]) <= tol * gold["loss"][k], (step, loss, gold["loss"][k])
         if trainable:
             l1, l2 = eng.get_lambda()
-            ltol = 1e-5 if step <= 10 else (2e-3 if step <= 100 else 0.05)  # absolute on lambda1, scaled for lambda2
+            ltol = 1e-5 if step <= 10 else (1e-3 if step <= 100 else 5e-3)  # absolute on lambda1, scaled for lambda2
             assert abs(l1 - gold["lambda1"][k]) <= ltol and abs(l2 - gold["lambda2"][k]) <= 0.1 * ltol, (step, l1, l2)
     pred, _ = eng.predict(g["X_star"], want_f=False)
     if trainable:

@@ -120,6 +120,19 @@ def reverse(theta, prob: Problem, cache, Ybar, Yxbar, Ytbar, Yxxbar):
     return np.concatenate([np.concatenate([gW[l].ravel(), gb[l].ravel()]) for l in range(L)])
 
 
+def reverse_step_hstream(a, Hx, Ht, Hxx, Hb, Hxb, Htb, Hxxb):
+    """The tanh reverse step of `reverse` restated in the OUTPUT streams (a, H_x, H_t, H_xx) of the layer instead of its
+    Z streams: with H_x = d1 Z_x, H_t = d1 Z_t, H_xx = d1 Z_xx + d2 Z_x^2, d2 = -2 a d1, d3 = -2 d1 (1 - 3 a^2) the
+    d3 Z_x^2 and d2 Z_xx terms collapse to -2 a H_xx - 2 H_x^2.  This is the form the CUDA kernels evaluate (their
+    stash holds the H streams); tests/test_oracle.py checks it against the Z-stream form above."""
+    d1 = 1.0 - a * a
+    Zxxb = d1 * Hxxb
+    Ztb = d1 * Htb
+    Zxb = d1 * Hxb - 4.0 * a * Hx * Hxxb
+    Zb = d1 * Hb - 2.0 * a * (Hx * Hxb + Ht * Htb + Hxx * Hxxb) - 2.0 * Hx * Hx * Hxxb
+    return Zb, Zxb, Ztb, Zxxb
+
+
 def burgers_residual(Y, Yx, Yt, Yxx, lam1, lam2):
     return Yt + lam1 * Y * Yx - lam2 * Yxx
 

@@ -85,6 +85,20 @@ def _loss_fp64(theta, c):
     return float(L.detach())
 
 
+def test_reverse_step_in_output_streams_equals_the_z_stream_form():
+    """the kernels' reverse step works on the stashed H streams (oracle.taylor.reverse_step_hstream): same numbers as
+    the Z-stream formulas of appendix A.2, also where tanh saturates"""
+    from oracle.taylor import reverse_step_hstream
+    rng = np.random.default_rng(5)
+    z, zx, zt, zxx, hb, hxb, htb, hxxb = rng.standard_normal((8, 20000)) * np.array([[3.0]] + [[1.5]] * 7)
+    a = np.tanh(z)
+    d1 = 1 - a * a; d2 = -2 * a * d1; d3 = -2 * d1 * (1 - 3 * a * a)
+    ref = (d1 * hb + d2 * (zx * hxb + zt * htb + zxx * hxxb) + d3 * zx * zx * hxxb, d1 * hxb + 2 * d2 * zx * hxxb, d1 * htb, d1 * hxxb)
+    got = reverse_step_hstream(a, d1 * zx, d1 * zt, d1 * zxx + d2 * zx * zx, hb, hxb, htb, hxxb)
+    for r, g in zip(ref, got):
+        assert np.abs(r - g).max() <= 1e-13 * max(np.abs(r).max(), 1.0)
+
+
 def test_fp32_graph_is_within_parity_budget_of_fp64():
     """the noise floor of an fp32 evaluation of the reference graph sits well under the 1e-5 parity target"""
     c = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V4, 100, 2000, seed=3)

@@ -694,7 +694,10 @@ static int timing_event(pinn_handle_t h, cudaEvent_t* out) {
 
 // the squared data term rides inside the fused kernel (extra batches); V1's un-squared norm needs ||r|| first
 static bool fused_handles_data(const pinn_handle_s* h) {
-  return h->fused.enabled && h->cfg.loss != PINN_LOSS_V1_INF_L2 && h->n_u > 0 && h->data_weight != 0.0f;
+  if (!h->fused.enabled || h->n_u <= 0 || h->data_weight == 0.0f) return false;
+  // V1's un-squared norm rides along when every warp gets one batch at most (the reference's sizes: 10 456 + 100 points)
+  if (h->cfg.loss == PINN_LOSS_V1_INF_L2) return h->feed_chunks <= 1 && fused_v1_fits(h->fused, h->n_f, h->n_u);
+  return true;
 }
 
 // same for the generic kernel's training pass (dual launch) when neither the fused nor the tensor kernel takes the batch
@@ -736,7 +739,8 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
     }
     const int64_t nfg = h->nf_global > 0 ? h->nf_global : h->n_f;
     const float* l1 = (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr;
-    const float data_c = with_data ? h->data_weight / (float)h->n_u : 0.f;
+    const bool v1 = with_data && h->cfg.loss == PINN_LOSS_V1_INF_L2;
+    const float data_c = !with_data ? 0.f : (v1 ? 0.5f : h->data_weight / (float)h->n_u);
     if (h->feed_chunks > 1 && mode == GEN_MODE_TRAIN && admm_op == 0) {
       // host-fed batch: one launch per chunk as soon as its copy has landed, accumulators carried over, the data
       // term rides with the last chunk, one reduction (+ Adam) at the end
@@ -761,7 +765,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
       rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f, nfg, mode, l1,
                      state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr,
                      with_data ? h->d_Xu : nullptr, with_data ? h->d_u : nullptr, h->n_u, data_c, h->d_packed, ad, e0, e1,
-                     h->stream, h->err);
+                     h->stream, h->err, 0, 0, (v1 && mode == GEN_MODE_TRAIN) ? h->data_weight : 0.f);
     }
     if (rc) return rc;
     h->launches += 2;

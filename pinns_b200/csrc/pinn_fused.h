@@ -38,4 +38,7 @@ int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const floa
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
               float* f_out, const float* Xu, const float* ud, int64_t n_u, float data_c, float* packed, const AdamFused& ad,
               cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream, std::string& err, int accumulate = 0,
-              int grid_fixed = 0);
+              int grid_fixed = 0, float v1_data_weight = 0.f);
+// v1_data_weight != 0: the data batches carry INF-L2's UN-squared norm (pass data_c = 0.5): they must own their warps
+// (n/32 + n_u/32 batches <= grid x warps) and the reduction scales their gradient by v1_data_weight / ||r||.
+bool fused_v1_fits(const FusedState& fs, int64_t n, int64_t n_u);

@@ -219,3 +219,34 @@ def test_host_feed_in_chunks_equals_resident_batch(loss, n_f):
     assert abs(outs[0][0] - outs[1][0]) <= 2e-6 * abs(outs[0][0])
     assert rel_err(outs[1][1], outs[0][1]) <= 5e-6
     assert rel_err(thetas[1] - c["theta"], thetas[0] - c["theta"]) <= 1e-3   # Adam's first step is +-lr per parameter
+
+
+def test_v1_norm_inside_the_fused_pass_and_its_fallback():
+    """INF-L2's un-squared data norm (appendix A.3 V1) rides inside the fused pass when every warp has one batch at most
+    (data batches own their accumulator regions, the reduction divides by ||r||); larger jobs take the separate data
+    pass.  Both agree with the oracle, an Adam step follows the oracle, and zero misfit gives tf.norm's NaN gradient."""
+    c = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V1, 100, 10456, seed=31)
+    ref = tg.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], c["X_f"])
+    eng = make_engine(c)                                  # 327 + 4 batches: inline
+    assert eng.kernel_path == "fused"
+    n0 = eng.launch_count
+    loss, grad = eng.loss_grad()
+    assert eng.launch_count - n0 == 2                     # one kernel + one reduction: no separate data pass
+    assert abs(loss - ref.loss) <= TOL * abs(ref.loss) and rel_err(grad, ref.grad) <= TOL
+    opt = TF1Adam(c["theta"].size)
+    th1 = opt.step(c["theta"].astype(np.float64), ref.grad)
+    eng.adam_steps(1)
+    assert rel_err(eng.get_params() - c["theta"], th1 - c["theta"]) <= 1e-4
+    # fallback: more batches than warps
+    big = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V1, 100, 148 * 8 * 32 + 5, seed=32)
+    refb = tg.evaluate(big["theta"], big["prob"], big["X_u"], big["u"], big["X_f"])
+    engb = make_engine(big)
+    lossb, gradb = engb.loss_grad()
+    assert abs(lossb - refb.loss) <= TOL * abs(refb.loss) and rel_err(gradb, refb.grad) <= TOL
+    # zero misfit on the inline path
+    small = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V1, 16, 64, seed=3)
+    e0 = make_engine(small)
+    u_self, _ = e0.predict(small["X_u"], want_f=False)    # same kernel family as the data batches -> exact zero
+    e0.set_data(small["X_u"], u_self.astype(np.float64))
+    l0, g0 = e0.loss_grad()
+    assert np.isfinite(l0) and np.isnan(g0).any()

@@ -250,3 +250,15 @@ def test_v1_norm_inside_the_fused_pass_and_its_fallback():
     e0.set_data(small["X_u"], u_self.astype(np.float64))
     l0, g0 = e0.loss_grad()
     assert np.isfinite(l0) and np.isnan(g0).any()
+
+
+def test_tensor_path_run_to_run_determinism():
+    """tcgen05 path: per-CTA partial gradients are updated with red.global.add by a fixed thread per element and summed
+    over CTAs in fixed order -> bit-identical loss and gradient from run to run"""
+    layers = [2] + [64] * 4 + [1]
+    c = make_case(tg.PDE_BURGERS, layers, tg.LOSS_V4, 50, 40000, seed=9)
+    eng = make_engine(c, path="tensor")
+    assert eng.kernel_path == "tensor"
+    l1, g1 = eng.loss_grad()
+    l2, g2 = eng.loss_grad()
+    assert l1 == l2 and np.array_equal(g1, g2)

@@ -21,6 +21,7 @@ struct FusedState {
   size_t smem = 0;
   float* d_stash = nullptr;   // per-thread activation stash (L2 resident)
   float* d_part = nullptr;    // [grid*warps][region] warp-private gradient / loss accumulators
+  float* d_zeros = nullptr;   // one accumulator tile of zeros (read by the first batch of a launch)
   int rvlen = 0;
   int region = 0;            // floats per warp-private accumulator region
 };

@@ -223,7 +223,12 @@ __device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const fl
     __syncthreads();  // stream s landed; every thread is past stream s-1, whose buffer may be refilled
     if (nbuf == 2 && s + 1 < S)
       stage_wg(smem + ((s + 1) & 1) * bufsz, hin.p[s + 1], hin.ld, np_in, zbT + (size_t)(s + 1) * T * ld_z, ld_z, np_out);
-    for (int task = crank * blockDim.x + threadIdx.x; task < ntasks; task += cs * blockDim.x) {
+    // fewer 8x8 tiles than threads in the cluster (625 for 200 x 200 at the reference's batch sizes): every rank takes a
+    // contiguous share instead of the first ranks taking a full block each and the rest idling
+    const int share = one_task ? (ntasks + cs - 1) / cs : (int)blockDim.x;
+    const int task0 = one_task ? (((int)threadIdx.x < share) ? crank * share + (int)threadIdx.x : ntasks)
+                               : crank * (int)blockDim.x + (int)threadIdx.x;
+    for (int task = task0; task < ntasks; task += cs * blockDim.x) {
       const int ig = task / ntj, jg = task % ntj;
       if (!one_task || s == 0) {
 #pragma unroll

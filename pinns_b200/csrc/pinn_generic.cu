@@ -355,6 +355,16 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
   float* gst = smem + S * kch * T;
   float* wsl = gst + warp * kch * 8;
   const int per_round = cs * nwarps;
+  // output group (8 neurons) of this warp in round r.  With fewer groups than warps in the cluster (25 for width 200 vs 64)
+  // every rank takes a contiguous share -- one or two warps per scheduler on all eight SMs -- instead of the first ranks
+  // filling all their warps and the rest idling
+  auto group_of = [&](int r, int rank, int w, int ngroups) {
+    if (ngroups <= per_round) {
+      const int share = (ngroups + cs - 1) / cs;
+      return (w < share) ? rank * share + w : ngroups;
+    }
+    return (r * cs + rank) * nwarps + w;
+  };
 
   // a training pass overwrites every weight / bias entry on the CTA's first tile (plain stores in weight_grad), so
   // only the lambda gradients and the sums need a zero; a forward-only pass leaves the gradient part defined as zero
@@ -428,7 +438,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
       const bool head = (l == L - 1);
       const int ngroups = np_out / 8;
       for (int r = 0; r * per_round < ngroups; ++r) {
-        const int jg = (r * cs + crank) * nwarps + warp;
+        const int jg = group_of(r, crank, warp, ngroups);
         const bool active = jg < ngroups;
         float acc[S][8];
         TRACE(100 + l);
@@ -609,7 +619,7 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
         const int ldz = net.npmax * T;
         const int ngroups = np_i / 8;
         for (int r = 0; r * per_round < ngroups; ++r) {
-          const int ig = (r * cs + crank) * nwarps + warp;
+          const int ig = group_of(r, crank, warp, ngroups);
           const bool active = ig < ngroups;
           float acc[S][8];
           gemm_staged<S>(zin, n_j, WT, np_i, ig, active, prestage || r > 0, act, wsl, kch, lane, acc);

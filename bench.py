@@ -181,7 +181,8 @@ def run_ours(args, rank, world, local_rank):
     eng.set_data(X_u, u)
     eng.adam_config(lr=1e-3)
     eng.sample_collocation(SEED, rank * nf, nf, nf_global)   # rank r owns counters [r*nf, (r+1)*nf)
-    stepper = DataParallelStepper(eng, rank, world)
+    # N > 1: the sum over ranks happens inside the reduction kernel through peer memory (NVLink), no collective launch
+    stepper = DataParallelStepper(eng, rank, world, peer_memory=(world > 1 and not args.nccl))
 
     def barrier():
         if world > 1:
@@ -275,7 +276,9 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_name(nf), "layers": LAYERS, "nf_per_gpu": nf, "nf_global": nf_global,
                    "l2_policy": "inputs (%d MB per GPU) larger than the 126 MB L2; no flush" % (nf * 8 // 2 ** 20),
-                   "parallelism": "dp%d" % world, "kernel_path": eng.kernel_path, "loss_after": loss_now},
+                   "parallelism": "dp%d" % world, "kernel_path": eng.kernel_path, "loss_after": loss_now,
+                   "rank_sum": ("peer-memory exchange inside the reduction kernel" if stepper.peer_memory else
+                                ("one NCCL allreduce of the packed vector" if world > 1 else "single GPU"))},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nf * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
@@ -294,6 +297,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nf", type=int, default=16 * 2 ** 20, help="collocation points per GPU")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: combine the ranks with one NCCL allreduce instead of peer memory")
     ap.add_argument("--cpu-points", type=int, default=2 ** 20, help="points per step of the cpu_baseline sample")
     ap.add_argument("--ref-points", type=int, default=2 ** 18, help="points per step of --impl reference")
     args = ap.parse_args()

@@ -122,6 +122,20 @@ int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device);
 /* scale applied to the data term of loss and gradient (1 on the rank that owns it, 0 elsewhere) */
 int pinn_set_data_weight(pinn_handle_t h, float w);
 
+/* ---- data-parallel exchange through peer memory (new capability; the reference has no data parallelism) ----
+ * One process per GPU on one NVLink / NVSwitch box.  Each rank exports a CUDA IPC handle of its receive buffer
+ * (pinn_comm_export, PINN_COMM_HANDLE_BYTES bytes), the host side gathers the handles of all ranks (any transport:
+ * torch.distributed, MPI, files) and hands the table to pinn_comm_attach.  From then on the reduction kernel of every
+ * TRAINING pass (pinn_loss_grad_device, pinn_adam_steps) stores its partial vector into every peer's slot, waits for
+ * the peers' flags and leaves the SUM over ranks in the packed vector -- the one sum-allreduce of the step without a
+ * separate collective -- and the fused Adam update applies to the summed gradient.  All ranks must run the same
+ * sequence of training passes.  Fused path only (pinn_kernel_path == PINN_PATH_FUSED); world <= 8.            */
+#define PINN_COMM_HANDLE_BYTES 64
+int pinn_comm_export(pinn_handle_t h, void* handle_out);
+int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles /* world x PINN_COMM_HANDLE_BYTES */);
+int pinn_comm_detach(pinn_handle_t h);
+int pinn_comm_status(pinn_handle_t h, int32_t* attached, int32_t* peer_timed_out);
+
 /* ---- the hot path: sess.run([loss, grads]) (INF-L2:135; L-BFGS callback AB-ADMM:216) ----
  * pinn_loss_grad_device leaves the PACKED vector in a device buffer:
  *   [0,P)      d loss / d theta (local sum over this handle's points)

@@ -61,6 +61,10 @@ PROTOTYPES = {
     "pinn_set_data": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "pinn_set_collocation": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
     "pinn_feed_collocation": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64]),
+    "pinn_comm_export": (C.c_int, [_H, C.c_void_p]),
+    "pinn_comm_attach": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "pinn_comm_detach": (C.c_int, [_H]),
+    "pinn_comm_status": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pinn_sample_collocation": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "pinn_get_collocation": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "pinn_set_data_weight": (C.c_int, [_H, C.c_float]),

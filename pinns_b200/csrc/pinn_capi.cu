@@ -73,6 +73,18 @@ struct pinn_handle_s {
   std::vector<cudaEvent_t> feed_ev;
   std::vector<int64_t> feed_first;
   int feed_chunks = 0;
+
+  // peer-memory exchange of the packed vector (pinn_comm_*): own receive buffer + the peers' buffers opened through CUDA IPC
+  struct {
+    bool attached = false;
+    int rank = 0, world = 1;
+    void* own = nullptr;                 // [2][PINN_MAX_RANKS][rvlen_pad] floats | [2][PINN_MAX_RANKS][nchunks] flags
+    void* opened[PINN_MAX_RANKS] = {};
+    size_t slot_bytes = 0;
+    int rvlen_pad = 0, nchunks = 0;
+    unsigned seq = 0;
+    int* d_hang = nullptr;
+  } comm;
 };
 
 static std::string g_create_err;
@@ -414,6 +426,9 @@ int pinn_destroy(pinn_handle_t h) {
     cudaEventDestroy(h->feed_start);
   }
   for (cudaEvent_t e : h->feed_ev) cudaEventDestroy(e);
+  pinn_comm_detach(h);
+  if (h->comm.own) cudaFree(h->comm.own);
+  if (h->comm.d_hang) cudaFree(h->comm.d_hang);
   float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
                    h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
                    h->d_l1sum, h->d_data_loss};
@@ -714,6 +729,23 @@ static float adam_next_alpha(pinn_handle_s* h) {
   return (float)((double)h->lr * std::sqrt(1.0 - h->b2pow) / (1.0 - h->b1pow));
 }
 
+// the exchange descriptor of the next reduction (null when this handle is not part of a peer-memory group)
+static const FusedComm* next_comm(pinn_handle_s* h, int mode, FusedComm& cm) {
+  if (!h->comm.attached || h->comm.world <= 1 || mode != GEN_MODE_TRAIN) return nullptr;
+  cm.world = h->comm.world;
+  cm.rank = h->comm.rank;
+  for (int r = 0; r < cm.world; ++r) {
+    char* base = static_cast<char*>(r == cm.rank ? h->comm.own : h->comm.opened[r]);
+    cm.slot[r] = reinterpret_cast<float*>(base);
+    cm.flag[r] = reinterpret_cast<unsigned*>(base + h->comm.slot_bytes);
+  }
+  cm.seq = ++h->comm.seq;
+  cm.rvlen_pad = h->comm.rvlen_pad;
+  cm.nchunks = h->comm.nchunks;
+  cm.hang = h->comm.d_hang;
+  return &cm;
+}
+
 static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam = false) {
   const bool state = loss_uses_state(h->cfg.loss) || admm_op != 0;
   if (state) {
@@ -739,6 +771,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
     }
     const int64_t nfg = h->nf_global > 0 ? h->nf_global : h->n_f;
     const float* l1 = (h->cfg.loss == PINN_LOSS_V3_L1SQ && mode == GEN_MODE_TRAIN) ? h->d_l1sum : nullptr;
+    FusedComm cm;
     const bool v1 = with_data && h->cfg.loss == PINN_LOSS_V1_INF_L2;
     const float data_c = !with_data ? 0.f : (v1 ? 0.5f : h->data_weight / (float)h->n_u);
     if (h->feed_chunks > 1 && mode == GEN_MODE_TRAIN && admm_op == 0) {
@@ -754,7 +787,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
                        state ? h->d_z + a : nullptr, state ? h->d_gamma + a : nullptr, 0, nullptr, nullptr,
                        (with_data && last) ? h->d_Xu : nullptr, (with_data && last) ? h->d_u : nullptr, h->n_u, data_c,
                        last ? h->d_packed : nullptr, ad, c == 0 ? e0 : nullptr, last ? e1 : nullptr, h->stream, h->err,
-                       /*accumulate=*/c > 0, /*grid_fixed=*/h->fused.grid);
+                       /*accumulate=*/c > 0, /*grid_fixed=*/h->fused.grid, 0.f, last ? next_comm(h, mode, cm) : nullptr);
         h->launches += 1;
       }
       if (rc) return rc;
@@ -765,7 +798,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
       rc = fused_run(h->fused, h->net, make_loss_coef(h, h->cfg.loss), h->d_theta, h->d_Xf, h->n_f, nfg, mode, l1,
                      state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr,
                      with_data ? h->d_Xu : nullptr, with_data ? h->d_u : nullptr, h->n_u, data_c, h->d_packed, ad, e0, e1,
-                     h->stream, h->err, 0, 0, (v1 && mode == GEN_MODE_TRAIN) ? h->data_weight : 0.f);
+                     h->stream, h->err, 0, 0, (v1 && mode == GEN_MODE_TRAIN) ? h->data_weight : 0.f, next_comm(h, mode, cm));
     }
     if (rc) return rc;
     h->launches += 2;
@@ -1050,6 +1083,76 @@ int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int
   if (z) CK(cudaMemcpyAsync(h->d_z, z, bytes, k, h->stream));
   if (gamma) CK(cudaMemcpyAsync(h->d_gamma, gamma, bytes, k, h->stream));
   if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  return PINN_OK;
+}
+
+/* ---- peer-memory exchange group (one process per GPU; buffers shared through CUDA IPC) ---- */
+int pinn_comm_export(pinn_handle_t h, void* handle_out) {
+  if (!h || !handle_out) return PINN_E_INVALID;
+  REQUIRE(h->fused.enabled, PINN_E_STATE, "pinn_comm_export: the peer-memory exchange lives in the fused path's reduction");
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->comm.own) {
+    h->comm.rvlen_pad = (h->rvlen + 31) / 32 * 32;
+    h->comm.nchunks = h->fused.region / 32;
+    h->comm.slot_bytes = (size_t)2 * PINN_MAX_RANKS * h->comm.rvlen_pad * sizeof(float);
+    const size_t bytes = h->comm.slot_bytes + (size_t)2 * PINN_MAX_RANKS * h->comm.nchunks * sizeof(unsigned);
+    CK(cudaMalloc(&h->comm.own, bytes));
+    CK(cudaMemset(h->comm.own, 0, bytes));
+    CK(cudaMalloc(&h->comm.d_hang, sizeof(int)));
+    CK(cudaMemset(h->comm.d_hang, 0, sizeof(int)));
+    CK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->comm.own));
+  static_assert(sizeof(ipc) == PINN_COMM_HANDLE_BYTES, "CUDA IPC handle size");
+  memcpy(handle_out, &ipc, sizeof(ipc));
+  return PINN_OK;
+}
+
+int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles) {
+  if (!h || !handles) return PINN_E_INVALID;
+  REQUIRE(h->comm.own, PINN_E_STATE, "pinn_comm_attach: call pinn_comm_export first");
+  REQUIRE(world >= 1 && world <= PINN_MAX_RANKS && rank >= 0 && rank < world, PINN_E_INVALID, "pinn_comm_attach: bad rank / world");
+  CK(cudaSetDevice(h->cfg.device));
+  const char* hs = static_cast<const char*>(handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, hs + (size_t)r * PINN_COMM_HANDLE_BYTES, sizeof(ipc));
+    CK(cudaIpcOpenMemHandle(&h->comm.opened[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+  }
+  h->comm.rank = rank;
+  h->comm.world = world;
+  h->comm.seq = 0;
+  h->comm.attached = true;
+  return PINN_OK;
+}
+
+int pinn_comm_detach(pinn_handle_t h) {
+  if (!h) return PINN_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < PINN_MAX_RANKS; ++r)
+    if (h->comm.opened[r]) {
+      cudaIpcCloseMemHandle(h->comm.opened[r]);
+      h->comm.opened[r] = nullptr;
+    }
+  h->comm.attached = false;
+  return PINN_OK;
+}
+
+int pinn_comm_status(pinn_handle_t h, int32_t* attached, int32_t* hang) {
+  if (!h) return PINN_E_INVALID;
+  if (attached) *attached = h->comm.attached ? 1 : 0;
+  if (hang) {
+    *hang = 0;
+    if (h->comm.d_hang) {
+      int v = 0;
+      CK(cudaMemcpyAsync(&v, h->comm.d_hang, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      *hang = v;
+    }
+  }
   return PINN_OK;
 }
 

@@ -12,6 +12,20 @@ struct AdamFused {
   float alpha = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
 };
 
+// Peer-memory exchange of the packed vector inside the reduction kernel (one process per GPU, buffers shared through
+// CUDA IPC over NVLink / NVSwitch): every rank stores its partial elements straight into every peer's receive slot,
+// raises a per-chunk flag there, waits for the peers' flags and sums the slots in rank order -- the sum-allreduce of the
+// data-parallel step without a separate collective launch (pinn_capi.cu: pinn_comm_*).
+constexpr int PINN_MAX_RANKS = 8;
+struct FusedComm {
+  int world = 1, rank = 0;
+  float* slot[PINN_MAX_RANKS] = {};      // receive buffer of rank r as mapped into THIS process: [2 parities][world][rvlen_pad]
+  unsigned* flag[PINN_MAX_RANKS] = {};   // flags of rank r: [2][world][nchunks]
+  unsigned seq = 0;                      // number of this exchange (1, 2, ...): flag value and parity
+  int rvlen_pad = 0, nchunks = 0;
+  int* hang = nullptr;                   // set when a peer's flag never arrives (bounded spin)
+};
+
 struct FusedState {
   bool enabled = false;
   int hidden = 0;        // hidden width (all hidden layers equal)
@@ -39,7 +53,7 @@ int fused_run(FusedState& fs, const NetDesc& net, const LossCoef& lc, const floa
               int64_t nf_global, int mode, const float* l1_sum, float* z, float* gamma, int admm_op, float* u_out,
               float* f_out, const float* Xu, const float* ud, int64_t n_u, float data_c, float* packed, const AdamFused& ad,
               cudaEvent_t ev_before, cudaEvent_t ev_after, cudaStream_t stream, std::string& err, int accumulate = 0,
-              int grid_fixed = 0, float v1_data_weight = 0.f);
+              int grid_fixed = 0, float v1_data_weight = 0.f, const FusedComm* comm = nullptr);
 // v1_data_weight != 0: the data batches carry INF-L2's UN-squared norm (pass data_c = 0.5): they must own their warps
 // (n/32 + n_u/32 batches <= grid x warps) and the reduction scales their gradient by v1_data_weight / ||r||.
 bool fused_v1_fits(const FusedState& fs, int64_t n, int64_t n_u);

@@ -4,8 +4,12 @@ data parallelism -- SURVEY.md sections 2.3, 8e).
 One process per GPU.  Collocation points are split into contiguous per-rank shards (or each
 rank draws the counter range [first, first+n) of the job-wide Philox stream), theta / Adam
 moments are replicated, and the packed vector [grad | dlambda | partial sums] is combined by
-ONE sum-allreduce (NCCL over NVLink on GPUs; gloo in the CPU tests) per step.  The data term
-lives on rank 0 only (data_weight 0 elsewhere) so the sum counts it once.
+ONE sum over ranks per step.  On the fused path that sum happens INSIDE the reduction kernel:
+every rank stores its partial vector into its peers' receive slots over NVLink (buffers shared
+through CUDA IPC), waits for their flags and adds the slots in rank order, so a step is two
+launches (residual+grad kernel, reduction+exchange+Adam) and no collective call
+(`attach_peer_memory`).  Everywhere else it is one sum-allreduce (NCCL on GPUs, gloo in the CPU
+tests).  The data term lives on rank 0 only (data_weight 0 elsewhere) so the sum counts it once.
 """
 from __future__ import annotations
 
@@ -32,15 +36,32 @@ def allreduce_sum_(tensor, group=None):
     return tensor
 
 
-class DataParallelStepper:
-    """Drives one Engine per rank: loss+grad kernel -> one allreduce -> replicated Adam update."""
+def attach_peer_memory(engine, rank: int, world: int, group=None) -> bool:
+    """Gathers the engines' CUDA IPC handles over the process group and joins them into one peer-memory exchange group.
+    Returns False (and changes nothing) when the engine is not on the fused path, the job has one rank or more than
+    eight, or the L1^2 loss needs its scalar allreduce between two passes."""
+    import torch.distributed as dist
+    ok = (world > 1 and world <= 8 and engine.kernel_path == "fused" and not eng_loss_is_l1(engine)
+          and dist.is_available() and dist.is_initialized())
+    if not ok:
+        return False
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.comm_export(), group=group)
+    engine.comm_attach(rank, world, handles)
+    dist.barrier(group=group)          # every rank has mapped its peers before anybody stores into them
+    return True
 
-    def __init__(self, engine, rank: int = 0, world: int = 1, group=None):
+
+class DataParallelStepper:
+    """Drives one Engine per rank: loss+grad kernel -> sum over ranks -> replicated Adam update."""
+
+    def __init__(self, engine, rank: int = 0, world: int = 1, group=None, peer_memory: bool = False):
         self.engine = engine
         self.rank, self.world, self.group = rank, world, group
         engine.set_data_weight(data_weight(rank))
         self._packed = engine.packed_tensor() if world > 1 else None
         self._l1 = None
+        self.peer_memory = bool(peer_memory) and attach_peer_memory(engine, rank, world, group)
 
     def loss_grad_device(self):
         eng = self.engine
@@ -50,11 +71,14 @@ class DataParallelStepper:
             if self._l1 is None:
                 self._l1 = eng.device_view(ptr, 1)
             allreduce_sum_(self._l1, self.group)
-        eng.loss_grad_device()
-        if self.world > 1:
+        eng.loss_grad_device()        # with peer memory attached the packed vector already holds the sum over ranks
+        if self.world > 1 and not self.peer_memory:
             allreduce_sum_(self._packed, self.group)
 
     def adam_step(self):
+        if self.peer_memory:
+            self.engine.adam_steps(1)  # residual+grad kernel, then ONE kernel: reduction + exchange + Adam
+            return
         self.loss_grad_device()
         self.engine.adam_apply()
 

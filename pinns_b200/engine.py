@@ -188,6 +188,32 @@ class Engine:
         self._ck(capi.lib.pinn_feed_collocation(self._h, C.c_void_p(ptr), int(n), int(nf_global)), "pinn_feed_collocation")
         self.n_f = int(n)
 
+    # ---- peer-memory exchange group (data-parallel sum inside the reduction kernel) ----
+    COMM_HANDLE_BYTES = 64
+
+    def comm_export(self) -> bytes:
+        """CUDA IPC handle of this engine's receive buffer (to be gathered over all ranks)."""
+        buf = C.create_string_buffer(self.COMM_HANDLE_BYTES)
+        self._ck(capi.lib.pinn_comm_export(self._h, buf), "pinn_comm_export")
+        return buf.raw
+
+    def comm_attach(self, rank: int, world: int, handles):
+        """handles: the comm_export() bytes of ranks 0..world-1 in rank order."""
+        table = b"".join(handles)
+        if len(table) != world * self.COMM_HANDLE_BYTES:
+            raise ValueError("need one %d-byte handle per rank" % self.COMM_HANDLE_BYTES)
+        self._ck(capi.lib.pinn_comm_attach(self._h, int(rank), int(world), C.c_char_p(table)), "pinn_comm_attach")
+        self.comm_attached = True
+
+    def comm_detach(self):
+        self._ck(capi.lib.pinn_comm_detach(self._h), "pinn_comm_detach")
+        self.comm_attached = False
+
+    def comm_status(self):
+        a, hg = C.c_int32(), C.c_int32()
+        self._ck(capi.lib.pinn_comm_status(self._h, C.byref(a), C.byref(hg)), "pinn_comm_status")
+        return bool(a.value), bool(hg.value)
+
     def sample_collocation(self, seed: int, first_index: int, n_f: int, nf_global: int = 0):
         self._ck(capi.lib.pinn_sample_collocation(self._h, int(seed), int(first_index), int(n_f), int(nf_global)),
                  "pinn_sample_collocation")

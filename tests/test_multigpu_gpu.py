@@ -1,5 +1,7 @@
-"""2-GPU test of the sharded path (skipped with fewer than two GPUs): one process per GPU, NCCL allreduce of the packed
-vector; the combined gradient and the Adam-updated parameters must equal the single-GPU result on the same points."""
+"""2-GPU test of the sharded path (skipped with fewer than two GPUs): one process per GPU; the packed vector is summed
+over ranks either by one NCCL allreduce or inside the reduction kernel through peer memory (CUDA IPC over NVLink); the
+combined gradient and the Adam-updated parameters must equal the single-GPU result on the same points, both ranks must
+hold the same bits, and a few more steps must keep them equal."""
 import os
 import socket
 
@@ -18,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_total, out):
+def _worker(rank, world, port, n_total, out, peer):
     import torch
     import torch.distributed as dist
     from pinns_b200 import Engine
@@ -37,19 +39,28 @@ def _worker(rank, world, port, n_total, out):
         eng.set_data(X_u, np.sin(X_u[:, 0:1]))
         first, cnt = shard_range(n_total, rank, world)
         eng.sample_collocation(1234, first, cnt, n_total)
-        st = DataParallelStepper(eng, rank, world)
+        st = DataParallelStepper(eng, rank, world, peer_memory=peer)
+        assert st.peer_memory == peer
         st.loss_grad_device()
         torch.cuda.synchronize()
         packed = eng.packed_tensor().cpu().numpy().copy()
         st.adam_step()
         theta = eng.get_params()
+        for _ in range(5):
+            st.adam_step()
+        theta6 = eng.get_params()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (packed.tobytes(), theta6.tobytes()))
+        same = all(g == gathered[0] for g in gathered)      # replicated state: identical bits on every rank
+        hang = eng.comm_status()[1] if peer else False
         if rank == 0:
-            out.put((packed, theta))
+            out.put((packed, theta, same, hang))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_gradient_equals_single_gpu():
+@pytest.mark.parametrize("peer", [False, True], ids=["nccl", "peer-memory"])
+def test_two_gpu_sharded_gradient_equals_single_gpu(peer):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -60,10 +71,11 @@ def test_two_gpu_sharded_gradient_equals_single_gpu():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, out, peer)) for r in range(2)]
     for p in procs:
         p.start()
-    packed2, theta2 = out.get(timeout=300)
+    packed2, theta2, same, hang = out.get(timeout=300)
+    assert same and not hang
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

@@ -242,6 +242,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
     e2e_value = nf_global / (e2e_ms * 1e-3)
 
+    if stepper.peer_memory and eng.comm_status()[1]:
+        raise RuntimeError("peer-memory exchange: a peer's flag did not arrive in time")
     if rank != 0:
         return
     # ---------------- roofline of the dominant kernel ----------------

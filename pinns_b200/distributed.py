@@ -45,9 +45,26 @@ def attach_peer_memory(engine, rank: int, world: int, group=None) -> bool:
           and dist.is_available() and dist.is_initialized())
     if not ok:
         return False
+    # every rank must end up in the same mode: a rank that cannot export / map (IPC disabled in its container, no P2P
+    # path) votes the whole group back to the allreduce
+    try:
+        mine = engine.comm_export()
+    except Exception:
+        mine = None
     handles = [None] * world
-    dist.all_gather_object(handles, engine.comm_export(), group=group)
-    engine.comm_attach(rank, world, handles)
+    dist.all_gather_object(handles, mine, group=group)
+    good = all(h is not None for h in handles)
+    if good:
+        try:
+            engine.comm_attach(rank, world, handles)
+        except Exception:
+            good = False
+    votes = [None] * world
+    dist.all_gather_object(votes, good, group=group)
+    if not all(votes):
+        if good:
+            engine.comm_detach()
+        return False
     dist.barrier(group=group)          # every rank has mapped its peers before anybody stores into them
     return True
 

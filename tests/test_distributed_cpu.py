@@ -87,3 +87,68 @@ def test_two_rank_allreduce_reproduces_single_process_gradient(loss):
     else:
         n_f = c["X_f"].shape[0]
         assert abs(packed[-2] + packed[-1] ** 2 / n_f - ref.loss) <= 1e-12 * abs(ref.loss)
+
+
+class _StubEngine:
+    """Stands in for the CUDA engine in the host-side group logic: exports a handle unless told to fail."""
+
+    def __init__(self, fail_export=False, path="fused", loss_kind="v4"):
+        self.fail_export, self.kernel_path, self.loss_kind = fail_export, path, loss_kind
+        self.attached = self.detached = False
+        self.weight = None
+
+    def set_data_weight(self, w):
+        self.weight = w
+
+    def packed_tensor(self):
+        return torch.zeros(4)
+
+    def comm_export(self):
+        if self.fail_export:
+            raise RuntimeError("IPC not available")
+        return b"\0" * 64
+
+    def comm_attach(self, rank, world, handles):
+        assert len(handles) == world and all(len(h) == 64 for h in handles)
+        self.attached = True
+
+    def comm_detach(self):
+        self.detached = True
+
+
+def _vote_worker(rank, world, port, scenario, out):
+    from pinns_b200.distributed import DataParallelStepper
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _StubEngine(fail_export=(scenario == "one-rank-fails" and rank == 1),
+                          path=("generic" if scenario == "not-fused" else "fused"),
+                          loss_kind=("v3" if scenario == "l1" else "v4"))
+        st = DataParallelStepper(eng, rank, world, peer_memory=True)
+        out.put((rank, st.peer_memory, eng.attached, eng.detached, eng.weight))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scenario,expect", [("all-good", True), ("one-rank-fails", False), ("not-fused", False), ("l1", False)])
+def test_peer_memory_group_is_all_or_nothing(scenario, expect):
+    """attach_peer_memory: every rank ends in the same mode; one rank that cannot export sends the whole group back to the
+    allreduce (nobody stays attached); paths / losses without the in-kernel exchange never try; data term on rank 0 only."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vote_worker, args=(r, 2, port, scenario, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, peer, attached, detached, weight in got:
+        assert peer == expect
+        assert weight == (1.0 if rank == 0 else 0.0)
+        if expect:
+            assert attached and not detached
+        else:
+            assert not attached or detached

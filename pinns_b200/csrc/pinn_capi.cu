@@ -1057,7 +1057,6 @@ int pinn_admm_update(pinn_handle_t h, int quirk) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_update: no collocation points set");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = PINN_OK;
   return residual_pass(h, GEN_MODE_FORWARD, quirk ? 3 : 2);
 }
 

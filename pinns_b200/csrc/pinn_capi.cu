@@ -1120,6 +1120,11 @@ int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles) 
     memcpy(&ipc, hs + (size_t)r * PINN_COMM_HANDLE_BYTES, sizeof(ipc));
     CK(cudaIpcOpenMemHandle(&h->comm.opened[r], ipc, cudaIpcMemLazyEnablePeerAccess));
   }
+  // a fresh numbering of the exchanges needs fresh flags (the peers store into this buffer only after the caller's
+  // barrier that follows the attach)
+  CK(cudaMemset(h->comm.own, 0, h->comm.slot_bytes + (size_t)2 * PINN_MAX_RANKS * h->comm.nchunks * sizeof(unsigned)));
+  CK(cudaMemset(h->comm.d_hang, 0, sizeof(int)));
+  CK(cudaDeviceSynchronize());
   h->comm.rank = rank;
   h->comm.world = world;
   h->comm.seq = 0;

@@ -305,7 +305,8 @@ class BurgersIdentification(_Base):
 
     def __init__(self, params, variant: str = "AB-ADMM", data=None, lambda_1: Optional[float] = None,
                  lambda_2: Optional[float] = None, trainable_lambda: bool = False, run: bool = True, seed: int = 1234,
-                 resample: str = "host", layers=None, verbose: bool = True, filename: Optional[str] = None):
+                 resample: str = "host", layers=None, verbose: bool = True, filename: Optional[str] = None,
+                 theta0=None):
         self.params = params
         self.variant = variant
         mat, vlayers, loss, self._resample_each_step, self._admm, self._lbfgs_after = _VARIANTS[variant]
@@ -327,7 +328,7 @@ class BurgersIdentification(_Base):
         self.engine = Engine(self.layers, self.lb, self.ub, pde="burgers", loss=loss, lambda1=lambda_1,
                              lambda2=lambda_2, rho=rho, trainable_lambda=trainable_lambda,
                              device=_first_gpu(getattr(params, "gpu", '0')))
-        self.engine.set_params(xavier_init_flat(self.layers, np.random.default_rng(seed)))
+        self.engine.set_params(xavier_init_flat(self.layers, np.random.default_rng(seed)) if theta0 is None else theta0)
         self.engine.set_data(self.X_u_train, self.u_train)
         self.engine.adam_config(lr=0.001)
         self._step_counter = 0
@@ -383,7 +384,9 @@ class BurgersIdentification(_Base):
 
     def train(self, nEpochs):                                                # AB-ADMM:200-252
         start_time = time.time()
-        epoch = 1
+        # the Abgrall scripts count `epoch = 1 .. nEpochs-1` (AB-ADMM:206-210), the two ID scripts
+        # `it = 0 .. nIter-1` (ID-L2b:156-159, ID-ADMMb:195-198): one Adam step more for the same argument
+        epoch = 0 if self.variant.startswith("ID-") else 1
         while epoch < nEpochs:
             if self._lbfgs_after is None or epoch <= self._lbfgs_after:
                 self.engine.adam_steps(1)
@@ -436,7 +439,7 @@ class EulerInference(_Base):
     """EUL:36-437: 1-D compressible Euler, outputs (rho,u,E), three ADMM residual blocks."""
 
     def __init__(self, params, data=None, run: bool = True, seed: int = 1234, resample: str = "host", layers=None,
-                 loss: str = "v5", verbose: bool = True, filename: Optional[str] = None):
+                 loss: str = "v5", verbose: bool = True, filename: Optional[str] = None, theta0=None):
         self.params = params
         self.verbose = verbose
         self._resample_mode = resample
@@ -451,7 +454,7 @@ class EulerInference(_Base):
         self._admm = (loss == "v5")
         self.engine = Engine(self.layers, self.lb, self.ub, pde="euler", loss=loss, rho=float(self.params.pen),
                              device=_first_gpu(getattr(params, "gpu", '0')))
-        self.engine.set_params(xavier_init_flat(self.layers, np.random.default_rng(seed)))
+        self.engine.set_params(xavier_init_flat(self.layers, np.random.default_rng(seed)) if theta0 is None else theta0)
         self.engine.set_data(self.X_data_train, np.hstack([self.rho, self.u, self.E]))
         self.engine.adam_config(lr=0.001)
         self._step_counter = 0

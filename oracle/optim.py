@@ -1,10 +1,11 @@
 """TF-1 Adam and the SciPy L-BFGS-B driver, restated.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: TensorFlow
-1.x (tf.train.AdamOptimizer, tf.contrib.opt.ScipyOptimizerInterface) is an
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  UNPINNED BY TENSORFLOW: TF 1.x
+(tf.train.AdamOptimizer, tf.contrib.opt.ScipyOptimizerInterface) is an
 un-vendored, un-pinned dependency of the reference; the update rules below are
 its documented algorithm, anchored on the call sites INF-L2:72-73 and
-AB-ADMM:66-72,:216.
+AB-ADMM:66-72,:216 (the TF-1 stand-in oracle/refshim restates the same rule, so
+the reference-run fixtures pin only how the scripts drive it).
 """
 from __future__ import annotations
 

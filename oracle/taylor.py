@@ -1,6 +1,7 @@
 """Independent numpy fp64 restatement: Taylor-forward + one reverse sweep.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Pinned against runs of the reference's own
+scripts over a TensorFlow-1 API stand-in (tests/test_reference_pin.py); TensorFlow itself unpinned.
 
 This is the schedule the CUDA kernels use, written out
 by hand with no autograd, so that it can be checked against ``oracle.tf_graph``

@@ -1,7 +1,9 @@
 """Op-for-op CPU restatement of the reference's TensorFlow-1 graph (torch autograd).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED: the
-reference pins no numbers for this path; TensorFlow 1.x is not installed.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Pinned against runs of the
+reference's own unmodified scripts over a TensorFlow-1 API stand-in
+(tests/golden/ref_*.npz, tests/test_reference_pin.py); TensorFlow itself is not
+installed, so the semantics of the TF ops remain restated from documentation.
 
 ``tf.gradients(y, x)[0]`` is restated as
 ``torch.autograd.grad(y, x, grad_outputs=ones_like(y), create_graph=True)[0]``

@@ -33,10 +33,20 @@ def test_loss_gradient_residuals_against_the_reference_graph(name):
     loss, grad = eng.loss_grad()
     P = eng.num_params
     assert abs(loss - fx["vec_loss"]) <= TOL * abs(fx["vec_loss"]), (loss, fx["vec_loss"])
-    # EUL: the ADMM adjoint seed pen*(f - z) + gamma with z ~ f cancels four digits of f (the fp64 oracle itself only
-    # reproduces this gradient to 1.4e-6 because of the reference's float32 constants); measured on B200 below 1e-4
-    gtol = 2e-4 if name == "EUL" else TOL
-    assert rel_err(grad[:P], fx["vec_grad"]) <= gtol, rel_err(grad[:P], fx["vec_grad"])
+    err = float(np.linalg.norm(grad[:P] - fx["vec_grad"]))
+    scale = float(np.linalg.norm(fx["vec_grad"]))
+    if "vec_z" in fx and name != "INF-ADMM":
+        # The scripts evaluate this gradient right after the z/gamma update on the same batch (AB-ADMM:225-226), where
+        # the adjoint seed rho*(f - z) + gamma collapses to +-1/N_f: three to four digits of f cancel, and a float32
+        # evaluation of the reference graph itself misses this vector by 8e-6 (ID-ADMMb) ... 1e-3 (EUL).  The error is
+        # therefore bounded against what is being cancelled -- the gradient of the bare penalty (rho/2)||f||^2 -- at a
+        # tenth of the fp32 budget.
+        zero = np.zeros_like(fx["vec_z"])
+        bare = tg.evaluate(np.float32(fx["stage%d_theta" % _last_stage(fx)]), p, fx["X_u"], fx["u_data"], fx["vec_X_f"],
+                           z=zero, gamma=zero)
+        scale = max(scale, 0.1 * float(np.linalg.norm(bare.grad)))
+    print("%s: gradient error %.2e of |g|, %.2e of the bound's scale" % (name, err / np.linalg.norm(fx["vec_grad"]), err / scale))
+    assert err <= TOL * scale, (err, scale)
     y, f = eng.predict(fx["vec_X_f"])
     assert max_rel_err(f, fx["vec_f"]) <= TOL
     y_u, _ = eng.predict(fx["X_u"], want_f=False)

@@ -19,6 +19,7 @@ noise.  Recorded per script:
                          (tf.gradients on the reference's loss tensor), residuals f_pred, u_pred -- the inputs of the
                          loss+grad parity tests
   csv_header, csv_rows   what record_data/save_data wrote (Dialect B)
+  lbfgs_*                AB-ADMM only: the reference's ScipyOptimizerInterface object run for LBFGS_ITERS iterations from vec_*
 
 /root/reference does not exist on the GPU box: tests read these files, never the reference.
 """
@@ -38,6 +39,7 @@ if ROOT not in sys.path:
 from oracle import run_reference as rr  # noqa: E402
 
 PRED_STRIDE = 7
+LBFGS_ITERS = 25
 
 # how each script is driven.  Dialect A drivers hard-code their arguments (1 epoch); stage 2 calls train() again.
 # Dialect B: positional argv of the driver block where it parses one, else the launch_NN_L2.py way (import the
@@ -205,6 +207,15 @@ def run_dialect_b(name, spec):
     if hasattr(m, "lambda_1"):
         out["lambda"] = np.array([m.sess.run(m.lambda_1)[0], m.sess.run(m.lambda_2)[0]], np.float64)
     _vectors(m, tf, out)
+    if hasattr(m, "lbfgs") and name == "AB-ADMM":
+        # the L-BFGS-B branch of AB-ADMM:213-216 (epoch > 50000) from the vec_* state, cut to LBFGS_ITERS iterations;
+        # every other option is the one the reference constructor passed (AB-ADMM:66-72)
+        m.lbfgs.options["maxiter"] = LBFGS_ITERS
+        res = m.lbfgs.minimize(m.sess, feed_dict=_feed(m))
+        out["lbfgs_options"] = json.dumps({k: float(v) for k, v in m.lbfgs.options.items()})
+        out["lbfgs_theta"] = rr.flat_params(m.sess, m.weights, m.biases)
+        out["lbfgs_loss"] = np.float64(res.fun)
+        out["lbfgs_nit"] = np.int64(res.nit)
     out["meta"] = json.dumps(dict(script=rr.SCRIPTS[name], dialect="B", params=params, stages=stages,
                                   pred_stride=PRED_STRIDE))
     return out

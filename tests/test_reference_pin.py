@@ -102,3 +102,25 @@ def test_live_reference_run_matches_the_oracle():
 def test_shim_initialiser_is_reproducible_without_the_reference():
     fx = load_ref_fixture("AB-ADMM")
     assert np.array_equal(rr.shim_initial_theta([int(n) for n in fx["layers"]]), fx["theta0"])
+
+
+def test_oracle_lbfgs_driver_follows_the_reference_scipy_interface():
+    """AB-ADMM:66-72,:216: the reference's ScipyOptimizerInterface object (options as its constructor passed them, cut
+    to 25 iterations) against oracle.optim.lbfgs_minimize from the same state: same packing order, float64 hand-off,
+    jac=True.  The oracle rounds theta through float32 at every evaluation (a tf.Variable's storage), the fixture's run
+    kept float64, so the two line searches drift apart slowly."""
+    import json
+    from oracle.optim import lbfgs_minimize
+    fx = load_ref_fixture("AB-ADMM")
+    prob = ref_problem("AB-ADMM", fx)
+    opts = {k: (v if k == "ftol" else int(v)) for k, v in json.loads(str(fx["lbfgs_options"])).items()}
+    assert {k: opts[k] for k in ("maxfun", "maxcor", "maxls", "ftol")} == dict(maxfun=50000, maxcor=50, maxls=50, ftol=1e-7)
+
+    def loss_grad(x):
+        ev = tg.evaluate(x, prob, fx["X_u"], fx["u_data"], fx["vec_X_f"], z=fx["vec_z"], gamma=fx["vec_gamma"])
+        return ev.loss, ev.grad
+
+    x, res = lbfgs_minimize(loss_grad, np.float32(fx["stage%d_theta" % _last_stage(fx)]).astype(np.float64), opts)
+    assert res.nit == int(fx["lbfgs_nit"])
+    assert abs(res.fun - fx["lbfgs_loss"]) <= 1e-4 * fx["lbfgs_loss"] and res.fun < 0.98 * fx["vec_loss"]
+    assert np.abs(x - fx["lbfgs_theta"]).max() <= 5e-4

@@ -387,28 +387,47 @@ class BurgersIdentification(_Base):
         # the Abgrall scripts count `epoch = 1 .. nEpochs-1` (AB-ADMM:206-210), the two ID scripts
         # `it = 0 .. nIter-1` (ID-L2b:156-159, ID-ADMMb:195-198): one Adam step more for the same argument
         epoch = 0 if self.variant.startswith("ID-") else 1
+        # The z/gamma update that closes an epoch (:225-226) and the Adam step that opens the next (:213) evaluate the
+        # same residuals: the update is held back (`pending`) and folded into the next step's training pass
+        # (engine.admm_adam_step, same bits), and flushed before anything else looks at the state.
+        pending = False
         while epoch < nEpochs:
             if self._lbfgs_after is None or epoch <= self._lbfgs_after:
-                self.engine.adam_steps(1)
+                if pending:
+                    self.engine.admm_adam_step()
+                    pending = False
+                else:
+                    self.engine.adam_steps(1)
             else:
+                if pending:
+                    self.engine.admm_update()
+                    pending = False
                 self.lbfgs_minimize(LBFGS_OPTIONS_AB_ADMM)
             if self._resample_each_step:
                 self._new_batch()
             if self._admm:
-                self.engine.admm_update()                                    # z_update, then gamma_update (:225-226)
+                pending = self._fold_admm                                     # z_update, then gamma_update (:225-226)
+                if not pending:
+                    self.engine.admm_update()
+            every = 1000 if (self._lbfgs_after is None or epoch < self._lbfgs_after) else 100
+            if pending and (epoch % 1000 == 0 or (self._record and epoch % every == 0)):
+                self.engine.admm_update()
+                pending = False
             if epoch % 1000 == 0:
                 elapsed = time.time() - start_time
                 loss_value = self.engine.loss_value()
                 if self.verbose:
                     print('It: %d, Loss: %.3e, Time: %.2f' % (epoch, loss_value, elapsed))
                 start_time = time.time()
-            every = 1000 if (self._lbfgs_after is None or epoch < self._lbfgs_after) else 100
             if self._record and epoch % every == 0:
                 self.record_data(epoch)
                 self.save_data()
             epoch += 1
+        if pending:
+            self.engine.admm_update()
 
     _record = False  # CSV dumps during training are opt-in here (the reference always writes them)
+    _fold_admm = True  # fold each epoch's z/gamma update into the next Adam step's pass (False: two passes, same bits)
 
     def predict(self, X_star):                                               # AB-ADMM:254-262
         return self.engine.predict(X_star, want_f=True)
@@ -513,11 +532,21 @@ class EulerInference(_Base):
     def train(self, nEpochs):                                                # EUL:217-258
         start_time = time.time()
         epoch = 1
+        pending = False   # a z/lagrange update waiting to be folded into the next Adam step's pass (same residuals, same bits)
         while epoch < nEpochs:
-            self.engine.adam_steps(1)
+            if pending:
+                self.engine.admm_adam_step()
+                pending = False
+            else:
+                self.engine.adam_steps(1)
             self._new_batch()
             if self._admm:
-                self.engine.admm_update()                                    # z1..3 then lagrange1..3 (:237-242)
+                pending = self._fold_admm                                     # z1..3 then lagrange1..3 (:237-242)
+                if not pending:
+                    self.engine.admm_update()
+            if pending and (epoch % 1000 == 0 or (self._record and epoch % 10000 == 0)):
+                self.engine.admm_update()
+                pending = False
             if epoch % 1000 == 0:
                 elapsed = time.time() - start_time
                 loss_value = self.engine.loss_value()
@@ -528,8 +557,11 @@ class EulerInference(_Base):
                 self.record_data(epoch)
                 self.save_data()
             epoch += 1
+        if pending:
+            self.engine.admm_update()
 
     _record = False
+    _fold_admm = True
 
     def predict(self, X_star):                                               # EUL:260-272: six arrays
         y, f = self.engine.predict(X_star, want_f=True)

@@ -133,3 +133,31 @@ def test_fixed_batch_adam_trajectory_tracks_the_oracle(which):
                "error_E": tg.relative_l2(g["E_star"], pred[:, 2:3])}
     for k, v in err.items():   # north_star: final relative L2 error within 10 % of the reference's
         assert abs(v - gold[k]) <= 0.10 * gold[k], (k, v, gold[k])
+
+
+@pytest.mark.parametrize("which", ["AB-ADMM", "ID-ADMMb", "EUL"])
+def test_folded_admm_update_is_bit_identical_to_two_passes(which):
+    """engine.admm_adam_step(): the z/gamma update closing epoch k rides in the training pass of epoch k+1's Adam step
+    (pinn_admm_adam_step, admm_op 4 of the fused and generic kernels) -- same theta, z, gamma bits as the reference's
+    order of separate passes (AB-ADMM:213-226, EUL:229-242), on both kernel families."""
+    from pinns_b200.models import BurgersIdentification, EulerInference, EulerParameters, Parameters
+    out = []
+    for fold in (False, True):
+        if which == "EUL":
+            class E(EulerParameters):
+                N_data = 200; N_f = 1000; pen = 40.0; epochs = 1; gpu = '0'
+            m = EulerInference(E(), data=os.path.join(GOLD, "data", "Abgrall_eulers.npz"), run=False, verbose=False)
+        else:
+            class P(Parameters):
+                N_u = 100; N_f = 1000; rho = 10.0; epochs = 1; gpu = '0'
+            data = {"AB-ADMM": "TwoSin_burgers_shock", "ID-ADMMb": "burgers_shock"}[which]
+            m = BurgersIdentification(P(), variant=which, data=os.path.join(GOLD, "data", data + ".npz"), run=False, verbose=False)
+        m._fold_admm = fold
+        launches0 = m.engine.launch_count
+        m.train(12)
+        z, g = m.engine.admm_state()
+        out.append((m.get_flat_params(), z, g, m.engine.loss_value(), m.engine.launch_count - launches0))
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(a, b)
+    assert out[0][3] == out[1][3]
+    assert out[1][4] < out[0][4]                                # and fewer kernel launches

@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "pinn_kernels.h"
+#include <cstdlib>
+
 #include "pinn_fused.h"
 #include "pinn_tensor.h"
 
@@ -178,7 +180,15 @@ static int gen_grid_for(const pinn_handle_s* h, int64_t n, int* cluster) {
   int64_t tiles = (n + PINN_TILE - 1) / PINN_TILE;
   if (tiles < 1) tiles = 1;
   int cs = 1;
-  while (cs < 8 && tiles * (cs * 2) <= h->gen_grid_max) cs *= 2;
+  static const int cs_max = [] {
+    const char* e = getenv("PINN_GEN_CLUSTER_MAX");  // measurement knob: cap on the CTAs that share a tile
+    const int v = e ? atoi(e) : 8;
+    return v >= 1 && v <= 8 ? v : 8;
+  }();
+  // Measured on B200 (scripts/cluster_size_probe.py, [2,200x5,3] and [2,200x8,1]): sharing a tile pays as long as every
+  // CTA still has an SM to itself; once two CTAs of a cluster's pace-setting member share an SM, 2 CTAs per tile are slower
+  // than 1 (94 tiles: 947 vs 779 us, 2363 vs 1910 us) while 4 per tile still win (47 tiles: 430 vs 482 us, 874 vs 1215 us).
+  while (cs < cs_max && tiles * (cs * 2) <= (cs == 1 ? (int64_t)h->num_sms : (int64_t)h->gen_grid_max)) cs *= 2;
   // narrow layers have too few 8-wide output groups to share
   int groups = 1;
   for (int l = 1; l <= h->net.L; ++l) groups = h->net.np[l] / 8 > groups ? h->net.np[l] / 8 : groups;

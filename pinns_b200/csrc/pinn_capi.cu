@@ -54,6 +54,7 @@ struct pinn_handle_s {
 
   float* d_scratch = nullptr;
   int gen_grid_max = 0;
+  int cluster_cap[9] = {0};  // clusters of c CTAs resident at one CTA per SM (pinn_generic_cluster_capacity)
   float* d_part = nullptr;
   float* d_part_data = nullptr;
   ScratchDesc sd_res, sd_data;
@@ -175,24 +176,44 @@ static int ensure_weights(pinn_handle_t h) {
   return PINN_OK;
 }
 
-// grid and cluster size of the generic kernel: with fewer tiles than CTA slots, a cluster of up to 8 CTAs shares a tile
-static int gen_grid_for(const pinn_handle_s* h, int64_t n, int* cluster) {
+// Grid and cluster size of the generic kernel.  With fewer tiles than SMs a cluster of cs CTAs shares a tile (the CTAs
+// split the output neurons / weight-gradient tiles and meet at cluster barriers).  Measured on B200
+// (scripts/cluster_size_probe.py, [2,200x5,3] and [2,200x8,1], logs under profiles/): a tile's time falls with cs
+// (1 : 2 : 3 : 4 CTAs = 3.2-4.2 : 2.1-2.8 : 1.3-1.4 : 1) as long as every CTA has an SM to itself; clusters beyond what the GPU
+// holds at one CTA per SM (a cluster lives inside one GPC: 148 / 74 / 45 / 33 / 26 / 22 / 15 / 15 clusters of 1..8 CTAs) share SMs with the others and the
+// kernel slows down by about (clusters / capacity + 0.4).  So: the cs that minimises  t(cs) * that penalty,  where
+// `extra_tiles` counts the data-term tiles that ride in the same launch (39 clusters for the reference's Euler batch:
+// cs = 3 fits, cs = 4 does not: 337 -> 294 us per step).
+static int gen_grid_for(const pinn_handle_s* h, int64_t n, int64_t extra_tiles, int* cluster) {
   int64_t tiles = (n + PINN_TILE - 1) / PINN_TILE;
   if (tiles < 1) tiles = 1;
-  int cs = 1;
   static const int cs_max = [] {
     const char* e = getenv("PINN_GEN_CLUSTER_MAX");  // measurement knob: cap on the CTAs that share a tile
     const int v = e ? atoi(e) : 8;
     return v >= 1 && v <= 8 ? v : 8;
   }();
-  // Measured on B200 (scripts/cluster_size_probe.py, [2,200x5,3] and [2,200x8,1]): sharing a tile pays as long as every
-  // CTA still has an SM to itself; once two CTAs of a cluster's pace-setting member share an SM, 2 CTAs per tile are slower
-  // than 1 (94 tiles: 947 vs 779 us, 2363 vs 1910 us) while 4 per tile still win (47 tiles: 430 vs 482 us, 874 vs 1215 us).
-  while (cs < cs_max && tiles * (cs * 2) <= (cs == 1 ? (int64_t)h->num_sms : (int64_t)h->gen_grid_max)) cs *= 2;
   // narrow layers have too few 8-wide output groups to share
   int groups = 1;
   for (int l = 1; l <= h->net.L; ++l) groups = h->net.np[l] / 8 > groups ? h->net.np[l] / 8 : groups;
-  while (cs > 1 && cs * 8 > groups * 2) cs /= 2;
+  static const double t_rel[9] = {0, 3.7, 2.5, 1.37, 1.0, 0.95, 0.9, 0.88, 0.85};
+  int cs = 1;
+  double best = 1e300;
+  for (int c = 1; c <= cs_max; ++c) {
+    if (c > 1 && c * 8 > groups * 2) break;
+    const int cap = h->cluster_cap[c] > 0 ? h->cluster_cap[c] : h->num_sms / c;
+    const double load = (double)(tiles + extra_tiles) / (double)cap;
+    const double cost = t_rel[c] * (load > 1.0 ? load + 0.4 : 1.0);  // measured: 1.15 -> 1.5x, 1.6 -> 1.9x, 2.1 -> 2.4x
+    if (cost < best * 0.999) {
+      best = cost;
+      cs = c;
+    }
+  }
+  static const int cs_force = [] {
+    const char* e = getenv("PINN_GEN_CLUSTER_FORCE");  // measurement knob
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= 8 ? v : 0;
+  }();
+  if (cs_force) cs = cs_force;
   *cluster = cs;
   const int64_t clusters = tiles < h->gen_grid_max / cs ? tiles : h->gen_grid_max / cs;
   return (int)(clusters * cs);
@@ -236,7 +257,7 @@ static int run_generic(pinn_handle_t h, int S, int mode, int loss, const float* 
   fill_gen_params(h, S, mode, loss, X, n, seed, u_out, f_out, admm_op, use_state, part, g);
   g.u_data = u_data;
   g.data_c = h->n_u > 0 ? h->data_weight / (float)h->n_u : 0.f;
-  const int grid = gen_grid_for(h, n, &g.cluster);
+  const int grid = gen_grid_for(h, n, 0, &g.cluster);
   CK(pinn_generic_launch(g, S, grid, h->stream));
   h->launches += 1;
   if (grid_out) *grid_out = grid / g.cluster;
@@ -250,7 +271,7 @@ static int run_generic_dual(pinn_handle_t h, int loss, int admm_op, bool use_sta
   if (rcw) return rcw;
   GenParams g, gd;
   fill_gen_params(h, h->S_res, GEN_MODE_TRAIN, loss, h->d_Xf, h->n_f, nullptr, nullptr, nullptr, admm_op, use_state, h->d_part, g);
-  const int grid_res = gen_grid_for(h, h->n_f, &g.cluster);
+  const int grid_res = gen_grid_for(h, h->n_f, (h->n_u + PINN_TILE - 1) / PINN_TILE, &g.cluster);
   const int cs = g.cluster;
   // data clusters: one per tile (when the residual job leaves too few free CTA slots the last ones simply queue)
   int64_t dclusters = (h->n_u + PINN_TILE - 1) / PINN_TILE;
@@ -382,6 +403,10 @@ int pinn_create(const pinn_config_t* cfg, pinn_handle_t* out) {
   }
   h->num_sms = prop.multiProcessorCount;
   h->gen_grid_max = h->num_sms * 2;
+  for (int c = 1; c <= 8; ++c) h->cluster_cap[c] = pinn_generic_cluster_capacity(c);
+  if (getenv("PINN_GEN_DEBUG"))
+    fprintf(stderr, "pinn_b200: cluster capacity at one CTA per SM: %d %d %d %d %d %d %d %d\n", h->cluster_cap[1], h->cluster_cap[2],
+            h->cluster_cap[3], h->cluster_cap[4], h->cluster_cap[5], h->cluster_cap[6], h->cluster_cap[7], h->cluster_cap[8]);
   h->sd_res = make_scratch_desc(net, h->S_res);
   h->sd_data = make_scratch_desc(net, 1);
 

@@ -816,3 +816,32 @@ cudaError_t pinn_generic_dual_launch(const GenParams& g_in, int S, int grid_res,
 #undef LAUNCH
   return cudaGetLastError();
 }
+
+// How many clusters of `cs` CTAs the GPU holds with ONE CTA per SM (a cluster lives inside one GPC, so this is the
+// sum over GPCs of floor(SMs / cs), e.g. ~34 for cs = 4 on 148 SMs, not 37): asked of the occupancy calculator with the
+// dynamic shared memory set so high that a second CTA cannot join an SM.  0 if the query fails.
+int pinn_generic_cluster_capacity(int cs) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cs * 64);
+  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.dynamicSmemBytes = 120 * 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaFuncSetAttribute(pinn_generic_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, pinn_generic_kernel<3>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+

@@ -47,6 +47,7 @@ struct GenParams {
 
 size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out);
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream);
+int pinn_generic_cluster_capacity(int cs);  // clusters of cs CTAs resident at one CTA per SM (0: unknown)
 cudaError_t pinn_generic_dual_launch(const GenParams& g, int S, int grid_res, const GenParams& gd, int grid_data,
                                      cudaStream_t stream);
 

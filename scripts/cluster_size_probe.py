@@ -4,7 +4,9 @@ from pinns_b200 import Engine
 from tests.helpers import rand_theta
 """Step time of the generic kernel's small-batch (cluster-per-tile) mode; PINN_GEN_CLUSTER_MAX caps the cluster size."""
 sizes = [int(a) for a in sys.argv[1:]] or [1000]
-cases = [("euler200x5", [2]+[200]*5+[3], "euler", "v5", 200, n) for n in sizes] + [("burgers200x8", [2]+[200]*8+[1], "burgers", "v4", 100, n) for n in sizes]
+import os
+ND = int(os.environ.get("PROBE_N_DATA", "200"))
+cases = [("euler200x5", [2]+[200]*5+[3], "euler", "v5", ND, n) for n in sizes] + [("burgers200x8", [2]+[200]*8+[1], "burgers", "v4", 100, n) for n in sizes]
 for name, layers, pde, loss, n_u, n_f in cases:
     eng = Engine(layers, [-1, 0], [1, 0.99], pde=pde, loss=loss, lambda2=0.01/np.pi, rho=40.0)
     eng.use_torch_stream()

@@ -24,7 +24,7 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 open('profiles/r01_launches.txt', 'w').write('\n'.join(out) + '\n')
 
 # ---- fused kernel ----
-rep = 'gpurun_out/prof_fused_r01c.ncu-rep'
+rep = 'gpurun_out/prof_fused_r01d.ncu-rep'
 txt = "# ncu --set full --clock-control none of pinn_fused_kernel<20,true>, 2 Mi points, B200 (round 1 final build: %s)\n" % rep
 txt += '\n'.join(l for l in sh('python scripts/ncu_summary.py %s 1' % rep).split('\n') if 'top source lines' not in l)
 txt += '\n'.join(sh('python scripts/ncu_sass.py %s 0' % rep).split('\n')[:45])
@@ -35,7 +35,8 @@ raw = list(csv.reader(io.StringIO(sh('ncu -i %s --page raw --csv' % rep))))
 d = dict(zip(raw[0], raw[2])); un = dict(zip(raw[0], raw[1]))
 val = lambda k: float(d[k].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}.get(un[k], 1)
 rd, wr, n = val('dram__bytes_read.sum'), val('dram__bytes_write.sum'), 2097152
-json.dump({"kernel": "pinn_fused_kernel<20,true>", "source": "ncu --set full --clock-control none, %s (summary: profiles/r01_fused_kernel_ncu.txt)" % rep,
+old = json.load(open('profiles/r01_fused_traffic.json')) if os.path.exists('profiles/r01_fused_traffic.json') else {}
+json.dump({"modes": old.get("modes", {}), "kernel": "pinn_fused_kernel<20,true>", "source": "ncu --set full --clock-control none, %s (summary: profiles/r01_fused_kernel_ncu.txt)" % rep,
            "points_in_capture": n, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_point": round((rd + wr) / n, 1), "algorithmic_hbm_bytes_per_point": 8,
            "note": "the excess is the per-point activation stash (2.24 KB written + re-read once) and the warp-private gradient accumulators (0.86 KB RMW per point); their working set (85 MB + 32 MB) sits at the edge of the 126 MB L2, so most writes are eventually written back. ~2.6 TB/s at 590 Mpts/s = 40 % of measured HBM bandwidth: not the bound (FMA pipe, shared-memory pipe and issue slots are, see the summary)."},
           open('profiles/r01_fused_traffic.json', 'w'), indent=1)

@@ -30,6 +30,8 @@ class FakeEngine:
     def loss_value(self): self.calls.append(("loss",)); return self._loss
     def admm_init(self): self.calls.append(("admm_init",))
     def admm_update(self, inf_admm_quirk=False): self.calls.append(("admm_update", inf_admm_quirk))
+    def admm_adam_step(self):  # one pass on the device; in the reference's order: z/gamma update, then the Adam step
+        self.calls.append(("admm_update", False)); self.calls.append(("adam", 1)); self.calls.append(("folded",))
     def predict(self, X, want_f=True):
         n = np.asarray(X).shape[0]
         no = self.layers[-1] if self.layers else 1
@@ -79,6 +81,12 @@ def test_identification_class_runs_inside_constructor_and_records_csv(fake, tmp_
     # AB-ADMM:206-226: epochs 1..5 -> Adam step, NEW batch, then z/gamma update on the new batch
     body = [c[0] for c in calls if c[0] in ("adam", "set_collocation", "admm_update")]
     assert body == ["set_collocation"] + ["adam", "set_collocation", "admm_update"] * 5
+    assert sum(c[0] == "folded" for c in calls) == 4         # updates 1..4 ride in the next Adam step's pass, the last one alone
+    m2 = models.BurgersIdentification(P(), variant="AB-ADMM", data=os.path.join(GOLD, "TwoSin_burgers_shock.npz"),
+                                      verbose=False, filename=out, run=False)
+    m2._fold_admm = False
+    m2.run_NN()
+    assert [c[0] for c in m2.engine.calls if c[0] in ("adam", "set_collocation", "admm_update", "folded")] == body
     assert m.X_star.shape == (513 * 101, 2) and np.isfinite(m.error_u)
     m.save_data(); m.save_data()
     lines = open(out[:-3] + "csv").read().splitlines()

@@ -168,8 +168,9 @@ int pinn_admm_init(pinn_handle_t h);          /* z = gamma = 1, then z <- f(thet
 int pinn_admm_update(pinn_handle_t h, int inf_admm_quirk); /* z_update then gamma_update on the current points */
 /* The z/gamma update that closes one epoch of the batch-ADMM loops and the Adam step that opens the next
  * (AB-ADMM:225-226 then :213; EUL:237-242 then :229) evaluate the same residuals: one training pass does both.
- * Equivalent, bit for bit, to pinn_admm_update(h, 0) followed by pinn_adam_steps(h, 1).                    */
-int pinn_admm_adam_step(pinn_handle_t h);
+ * Equivalent, bit for bit, to pinn_admm_update(h, inf_admm_quirk) followed by pinn_adam_steps(h, 1)
+ * (INF-ADMM:189-193 with inf_admm_quirk = 1).                                                            */
+int pinn_admm_adam_step(pinn_handle_t h, int inf_admm_quirk);
 int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device); /* [N_f, n_res] each */
 int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int on_device);
 

@@ -80,7 +80,7 @@ PROTOTYPES = {
     "pinn_predict": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_admm_init": (C.c_int, [_H]),
     "pinn_admm_update": (C.c_int, [_H, C.c_int]),
-    "pinn_admm_adam_step": (C.c_int, [_H]),
+    "pinn_admm_adam_step": (C.c_int, [_H, C.c_int]),
     "pinn_admm_get_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_admm_set_state": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_kernel_timing": (C.c_int, [_H, C.c_int]),

@@ -1015,23 +1015,25 @@ int pinn_adam_steps(pinn_handle_t h, int64_t n_steps) {
 
 // One epoch boundary of the batch-ADMM loops (AB-ADMM:213-226, EUL:229-242): the z/gamma update that closes epoch k and
 // the Adam step that opens epoch k+1 evaluate the same residuals f(theta, batch) -- one training pass does both
-// (admm_op 4: update first, then seed the reverse sweep with the new state).  Bit-identical to pinn_admm_update(h, 0)
-// followed by pinn_adam_steps(h, 1); the tcgen05 path and the multi-pass L1^2 loss take exactly that route.
-int pinn_admm_adam_step(pinn_handle_t h) {
+// (admm_op 4 / 5: update first, then seed the reverse sweep with the new state).  Bit-identical to pinn_admm_update(h, quirk)
+// followed by pinn_adam_steps(h, 1) -- INF-ADMM:189-193 with its double dual update when quirk is set; the tcgen05 path and the multi-pass L1^2 loss take exactly that route.
+int pinn_admm_adam_step(pinn_handle_t h, int quirk) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_admm_adam_step: no collocation points set");
-  REQUIRE(h->cfg.loss == PINN_LOSS_V5_ADMM, PINN_E_STATE, "pinn_admm_adam_step: the loss is not the batch-ADMM loss");
+  REQUIRE(h->cfg.loss == PINN_LOSS_V5_ADMM || h->cfg.loss == PINN_LOSS_V2_INF_ADMM, PINN_E_STATE,
+          "pinn_admm_adam_step: the loss is not an ADMM loss");
+  const int op = quirk ? 5 : 4;
   CK(cudaSetDevice(h->cfg.device));
   int rc = feed_join(h);
   if (rc) return rc;
   const bool tensor = !h->fused.enabled && h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS);
   if (tensor) {
-    rc = pinn_admm_update(h, 0);
+    rc = pinn_admm_update(h, quirk);
     return rc ? rc : pinn_adam_steps(h, 1);
   }
   const bool lane2 = h->fused.enabled && (fused_handles_data(h) || h->n_u == 0 || h->data_weight == 0.0f);
-  if (lane2) return residual_pass(h, GEN_MODE_TRAIN, 4, /*fuse_adam=*/true);
-  rc = residual_pass(h, GEN_MODE_TRAIN, 4);
+  if (lane2) return residual_pass(h, GEN_MODE_TRAIN, op, /*fuse_adam=*/true);
+  rc = residual_pass(h, GEN_MODE_TRAIN, op);
   if (rc) return rc;
   if (!(fused_handles_data(h) || generic_handles_data(h))) {
     rc = data_term(h, true);

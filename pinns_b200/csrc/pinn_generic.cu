@@ -295,11 +295,12 @@ __device__ __forceinline__ float seed_one(const GenParams& g, float f, float cB,
   if (admm && valid) {
     zz = g.z[idx];
     gg = g.gamma[idx];
-    if (g.admm_op == 4) {
+    if (g.admm_op >= 4) {
       // z/gamma update of the previous epoch folded into this training pass (AB-ADMM:225-226 and :213 of the next
       // iteration, EUL:237-242 and :229, evaluate the same f): update first, seed and loss terms see the new state
       const float rho = lc.rho;
       const float kappa = 1.0f / (rho * (float)g.nf_global);
+      if (g.admm_op == 5) gg = gg + rho * (f - zz);  // INF-ADMM:106-107: the dual advances inside z_update
       const float val = f + gg / rho;
       const float c1 = (val > kappa) ? 1.f : 0.f;
       const float c3 = (val < -1.0f * kappa) ? 1.f : 0.f;
@@ -332,7 +333,7 @@ __device__ __forceinline__ float seed_one(const GenParams& g, float f, float cB,
 
 // soft threshold + dual update (AB-ADMM:185-198,:132; INF-ADMM:205-215,:106-107; EUL:203-215,:137-139)
 __device__ __forceinline__ void admm_one(const GenParams& g, float f, int64_t idx) {
-  if (g.admm_op == 4) return;  // already applied inside seed_one
+  if (g.admm_op >= 4) return;  // already applied inside seed_one
   if (g.admm_op == 1) {  // z <- f(theta0)  (AB-ADMM:96-97)
     g.z[idx] = f;
     return;

@@ -36,7 +36,7 @@ struct GenParams {
   float* f_out;         // [N, n_res] or null
   float* z;             // ADMM state [N, n_res]
   float* gamma;
-  int admm_op;          // 0 none, 1 z <- f, 2 z/gamma update, 3 update with the INF-ADMM quirk, 4 update BEFORE the seed (training pass)
+  int admm_op;          // 0 none, 1 z <- f, 2 z/gamma update, 3 update with the INF-ADMM quirk, 4 update BEFORE the seed (training pass), 5 the same with the quirk
   float* scratch;
   float* part;          // [grid][rvlen] per-CTA partial packed vectors
   int rvlen;

@@ -314,10 +314,10 @@ class Engine:
     def admm_update(self, inf_admm_quirk: bool = False):
         self._ck(capi.lib.pinn_admm_update(self._h, int(inf_admm_quirk)), "pinn_admm_update")
 
-    def admm_adam_step(self):
+    def admm_adam_step(self, inf_admm_quirk: bool = False):
         """z/gamma update of the closing epoch + Adam step of the next one in a single training pass (both evaluate
         the same residuals; AB-ADMM:225-226 then :213).  Same bits as admm_update() followed by adam_steps(1)."""
-        self._ck(capi.lib.pinn_admm_adam_step(self._h), "pinn_admm_adam_step")
+        self._ck(capi.lib.pinn_admm_adam_step(self._h, int(inf_admm_quirk)), "pinn_admm_adam_step")
 
     def admm_state(self):
         z = np.empty((self.n_f, self.n_res), np.float32)

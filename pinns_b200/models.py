@@ -238,11 +238,21 @@ class PhysicsInformedNN_ADMM(_Base):
         start_time = time.time()
         iter_counter = 0
         loss_value = 1000
+        pending = False  # a z / multiplier update held back to ride in the next Adam step's pass (same residuals, same bits)
         while iter_counter < number_of_ADMM_iterations and abs(loss_value) > self.tol:
-            self.engine.adam_steps(1)
+            if pending:
+                self.engine.admm_adam_step(inf_admm_quirk=True)
+                pending = False
+            else:
+                self.engine.adam_steps(1)
             if iter_counter % number_of_w_optimization_steps == 0:
                 # z_update then lagrange_update; the graph quirk (:106-107) advances the multiplier twice
+                pending = self._fold_admm
+                if not pending:
+                    self.engine.admm_update(inf_admm_quirk=True)
+            if pending and iter_counter % 100 == 0:
                 self.engine.admm_update(inf_admm_quirk=True)
+                pending = False
             if iter_counter % 100 == 0:
                 time_elapsed = time.time() - start_time
                 loss_value = self.engine.loss_value()
@@ -251,8 +261,12 @@ class PhysicsInformedNN_ADMM(_Base):
                           % (filename, iter_counter, loss_value, time_elapsed, GPU_number))
                 start_time = time.time()
             iter_counter += 1
+        if pending:
+            self.engine.admm_update(inf_admm_quirk=True)
         self.loss_value = loss_value
         return iter_counter
+
+    _fold_admm = True
 
     def soft_thresholding(self):
         return self.engine.admm_state()[0]

@@ -30,8 +30,8 @@ class FakeEngine:
     def loss_value(self): self.calls.append(("loss",)); return self._loss
     def admm_init(self): self.calls.append(("admm_init",))
     def admm_update(self, inf_admm_quirk=False): self.calls.append(("admm_update", inf_admm_quirk))
-    def admm_adam_step(self):  # one pass on the device; in the reference's order: z/gamma update, then the Adam step
-        self.calls.append(("admm_update", False)); self.calls.append(("adam", 1)); self.calls.append(("folded",))
+    def admm_adam_step(self, inf_admm_quirk=False):  # one pass on the device; in the reference's order: update, then the Adam step
+        self.calls.append(("admm_update", inf_admm_quirk)); self.calls.append(("adam", 1)); self.calls.append(("folded",))
     def predict(self, X, want_f=True):
         n = np.asarray(X).shape[0]
         no = self.layers[-1] if self.layers else 1

@@ -135,6 +135,28 @@ def test_fixed_batch_adam_trajectory_tracks_the_oracle(which):
         assert abs(v - gold[k]) <= 0.10 * gold[k], (k, v, gold[k])
 
 
+def test_folded_admm_update_of_the_inference_class_is_bit_identical():
+    """INF-ADMM:189-193 (Adam step, then z_update + lagrange_update with the double dual update every w steps): the held-back
+    update rides in the next Adam step's pass (admm_op 5) -- same theta, z, multiplier and loss bits."""
+    from oracle import data as odata
+    from pinns_b200.models import PhysicsInformedNN_ADMM
+    sol = dict(np.load(os.path.join(GOLD, "data", "burgers_shock.npz")))
+    g = odata.burgers_inference_inputs(sol, N_u=100, N_f=2000)
+    for wsteps in (1, 3):
+        out = []
+        for fold in (False, True):
+            m = PhysicsInformedNN_ADMM(g["X_u"], g["u"], g["X_f"], [2] + [20] * 8 + [1], g["lb"], g["ub"], 0.0, 1, 0.5, 'f', '0',
+                                       verbose=False)
+            m._fold_admm = fold
+            n0 = m.engine.launch_count
+            m.train(14, wsteps, 'f', '0')
+            z, lag = m.engine.admm_state()
+            out.append((m.get_flat_params(), z, lag, m.loss_value, m.engine.launch_count - n0))
+        for a, b in zip(out[0][:3], out[1][:3]):
+            assert np.array_equal(a, b)
+        assert out[0][3] == out[1][3] and out[1][4] < out[0][4]
+
+
 @pytest.mark.parametrize("which", ["AB-ADMM", "ID-ADMMb", "EUL"])
 def test_folded_admm_update_is_bit_identical_to_two_passes(which):
     """engine.admm_adam_step(): the z/gamma update closing epoch k rides in the training pass of epoch k+1's Adam step

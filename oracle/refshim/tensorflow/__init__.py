@@ -105,10 +105,8 @@ class Tensor:
 def convert_to_tensor(v):
     if isinstance(v, Tensor):
         return v
-    val = _to_compute(v)
-    # constants are captured at graph-construction time, but re-cast if the compute dtype changes later
-    src = _np.asarray(v, dtype=_np.float64)
-    return Tensor(lambda: _to_compute(src) if val.dtype != _State.compute else val, [], "Const")
+    src = _np.array(v, dtype=_np.float64)      # captured at graph-construction time, like a tf constant
+    return Tensor(lambda: _to_compute(src), [], "Const")
 
 
 def _binary(fn, a, b, name):

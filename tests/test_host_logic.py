@@ -70,6 +70,23 @@ def test_inf_admm_updates_every_k_steps_with_the_graph_quirk(fake):
     assert seq.count(("admm_update", True)) == 3 and seq[1] == ("admm_update", True)
 
 
+def test_inference_admm_loop_order_with_and_without_the_folded_update(fake):
+    """INF-ADMM:189-193: Adam step, then (every w steps) z_update + lagrange_update, loss every 100 iterations.  The folded
+    form issues the same operations in the same order; an update due at a loss print is flushed before the loss is read."""
+    X_u = np.random.rand(10, 2); u = np.random.rand(10, 1); X_f = np.random.rand(50, 2)
+    seqs = []
+    for fold in (False, True):
+        m = models.PhysicsInformedNN_ADMM(X_u, u, X_f, [2, 20, 20, 1], np.zeros(2), np.ones(2), 0.0, 1, 0.5, 'f', '0', verbose=False)
+        m._fold_admm = fold
+        m.train(7, 2, 'f', '0')
+        seqs.append([c for c in m.engine.calls if c[0] in ("adam", "admm_update", "loss", "folded")])
+    plain = [c for c in seqs[0] if c[0] != "folded"]
+    assert [c[0] for c in plain] == ["adam", "admm_update", "loss", "adam", "adam", "admm_update", "adam", "adam", "admm_update",
+                                     "adam", "adam", "admm_update"]
+    assert all(c == ("admm_update", True) for c in plain if c[0] == "admm_update")          # the double dual update
+    assert [c for c in seqs[1] if c[0] != "folded"] == plain and sum(c[0] == "folded" for c in seqs[1]) == 2
+
+
 def test_identification_class_runs_inside_constructor_and_records_csv(fake, tmp_path):
     class P(models.Parameters):
         N_u = 50; N_f = 64; rho = 10.0; epochs = 6; gpu = '0'

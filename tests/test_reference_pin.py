@@ -15,6 +15,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import run_reference as rr
 from oracle import taylor
@@ -124,3 +125,29 @@ def test_oracle_lbfgs_driver_follows_the_reference_scipy_interface():
     assert res.nit == int(fx["lbfgs_nit"])
     assert abs(res.fun - fx["lbfgs_loss"]) <= 1e-4 * fx["lbfgs_loss"] and res.fun < 0.98 * fx["vec_loss"]
     assert np.abs(x - fx["lbfgs_theta"]).max() <= 5e-4
+
+
+@pytest.mark.parametrize("name", SCRIPTS)
+def test_float32_evaluation_noise_of_the_reference_graph_at_the_fixture_states(name):
+    """What a float32 evaluation of the reference graph ITSELF (the oracle's op-for-op restatement run in torch float32,
+    correctly rounded ops) makes of the fixture vectors.  Five scripts: loss, residuals and gradient to ~1e-7.  The three
+    batch-ADMM scripts evaluate their gradient right after the z/gamma update on the same batch, where the adjoint seed
+    rho (f - z) + gamma collapses to +-1/N_f and three to four digits of f cancel: there float32 itself is at 1e-5 .. 1e-3.
+    This is the yardstick behind the scale-aware gradient bound of tests/test_reference_parity_gpu.py."""
+    fx = load_ref_fixture(name)
+    prob = ref_problem(name, fx)
+    theta = np.float32(fx["stage%d_theta" % _last_stage(fx)])
+    ev = tg.evaluate(theta, prob, fx["X_u"], fx["u_data"], fx["vec_X_f"], z=fx.get("vec_z"), gamma=fx.get("vec_gamma"),
+                     dtype=torch.float32)
+    noise = rel_err(ev.grad, fx["vec_grad"])
+    assert abs(ev.loss - fx["vec_loss"]) <= 1e-6 * abs(fx["vec_loss"])
+    assert max_rel_err(ev.f, fx["vec_f"]) <= 1e-5
+    if name in ("ID-ADMMb", "AB-ADMM", "EUL"):
+        zero = np.zeros_like(fx["vec_z"])
+        bare = tg.evaluate(theta, prob, fx["X_u"], fx["u_data"], fx["vec_X_f"], z=zero, gamma=zero)
+        cancel = np.linalg.norm(bare.grad) / np.linalg.norm(fx["vec_grad"])
+        assert cancel > 500                                     # the gradient is what is left of a >500x larger one
+        assert 1e-6 < noise < 5e-3, noise
+        assert noise * np.linalg.norm(fx["vec_grad"]) <= 1e-6 * np.linalg.norm(bare.grad)
+    else:
+        assert noise <= 1e-6, noise

@@ -25,6 +25,10 @@ CASES = [
     ("euler-mse-200", tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_EULER_MSE, 200, 1000),
     ("euler-admm-200", tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_V6, 200, 1000),
     ("euler-admm-ragged", tg.PDE_EULER, [2, 30, 17, 3], tg.LOSS_V6, 11, 97),
+    # cluster sizes the capacity rule of gen_grid_for picks besides 1 / 3 / 4 / 6: 23 + 2 tiles -> 5 CTAs per tile,
+    # 10 + 2 tiles of a 256-wide net -> 8 CTAs per tile
+    ("euler-mse-200-cs5", tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_EULER_MSE, 50, 736),
+    ("burgers-v4-256-cs8", tg.PDE_BURGERS, [2, 256, 256, 256, 1], tg.LOSS_V4, 50, 320),
 ]
 
 

@@ -292,3 +292,23 @@ def test_tensor_path_run_to_run_determinism():
     l1, g1 = eng.loss_grad()
     l2, g2 = eng.loss_grad()
     assert l1 == l2 and np.array_equal(g1, g2)
+
+
+def test_state_and_argument_errors_are_reported_not_crashed():
+    """Error behaviour at the boundary: the reference lets TF raise (e.g. "You must feed a value for
+    placeholder"); here every entry point returns a negative PINN_E_* code with a message and the handle stays usable."""
+    from pinns_b200 import Engine
+    from pinns_b200._capi import PinnError
+    eng = Engine(B20, [-1.0, 0.0], [1.0, 0.99], loss="v4")
+    for call in (eng.loss_grad, lambda: eng.adam_steps(1), eng.admm_update, eng.loss_value):
+        with pytest.raises(PinnError) as e:                     # no collocation points fed yet
+            call()
+        assert "collocation" in str(e.value)
+    with pytest.raises(PinnError):
+        eng.set_collocation(np.zeros((0, 2)))                   # an empty feed is rejected, not launched
+    eng.set_collocation(np.random.default_rng(0).random((65, 2)))
+    with pytest.raises(PinnError) as e:
+        eng.admm_adam_step()                                    # folded ADMM step on a non-ADMM loss
+    assert "ADMM" in str(e.value)
+    loss, grad = eng.loss_grad()                                # the handle is still good
+    assert np.isfinite(loss) and np.isfinite(grad).all() and grad.shape == (eng.num_params,)

@@ -201,3 +201,28 @@ def test_philox_known_answer_and_sharding_invariance():
     assert np.array_equal(full, parts)
     assert full[:, 0].min() >= -1 and full[:, 0].max() < 1 and full[:, 1].min() >= 0 and full[:, 1].max() < 0.99
     assert abs(full[:, 0].mean()) < 0.1
+
+
+def test_autograd_vs_taylor_on_random_ragged_nets():
+    """Property test (hypothesis): any depth / ragged widths / batch sizes, every PDE x loss variant -- the two restatements
+    agree to rounding, so a bug would have to be made twice, independently, to slip through."""
+    from hypothesis import given, settings, strategies as st
+
+    burgers_losses = [tg.LOSS_V1, tg.LOSS_V2, tg.LOSS_V3, tg.LOSS_V4, tg.LOSS_V5]
+    euler_losses = [tg.LOSS_V6, tg.LOSS_EULER_MSE]
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(st.lists(st.integers(1, 19), min_size=1, max_size=5), st.booleans(), st.integers(0, 4), st.integers(1, 40),
+           st.integers(1, 70), st.integers(0, 10 ** 6))
+    def check(hidden, euler, which, n_u, n_f, seed):
+        pde = tg.PDE_EULER if euler else tg.PDE_BURGERS
+        loss = euler_losses[which % 2] if euler else burgers_losses[which]
+        layers = [2] + hidden + [3 if euler else 1]
+        c = make_case(pde, layers, loss, n_u, n_f, seed=seed)
+        a = tg.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], c["X_f"], c["z"], c["gamma"])
+        b = ty.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], c["X_f"], c["z"], c["gamma"])
+        assert abs(a.loss - b.loss) <= 1e-11 * abs(a.loss)
+        assert np.abs(a.grad - b.grad).max() <= 1e-10 * max(np.abs(a.grad).max(), 1e-30)
+        assert np.abs(a.f - b.f).max() <= 1e-11 * max(1.0, np.abs(a.f).max())
+
+    check()

@@ -269,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
                 "traffic_source": "profiles/r01_fused_traffic.json (ncu dram__bytes_read+write per point x points per launch)",
                 "hbm_algorithmic_bytes_per_point": 8}
     cpu = None
-    if world == 1 or True:
+    if world == 1:  # the CPU sample is timed on rank 0 at N = 1 only (bench contract); null in the scaling runs
         cpu = cpu_reference_run(steps=2, warmup=1, n_sample=args.cpu_points)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {

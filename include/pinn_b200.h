@@ -91,7 +91,7 @@ int pinn_synchronize(pinn_handle_t h);
 /* ---- introspection ---- */
 int pinn_num_params(pinn_handle_t h, int64_t* n_params);   /* P: weights + biases             */
 int pinn_packed_len(pinn_handle_t h, int64_t* n);          /* length of the packed vector below */
-int pinn_kernel_path(pinn_handle_t h, int32_t* path);      /* PINN_PATH_GENERIC, _FUSED or _TENSOR actually used */
+int pinn_kernel_path(pinn_handle_t h, int32_t* path);      /* the kernel family the CURRENT collocation batch runs on */
 int pinn_launch_count(pinn_handle_t h, int64_t* n);        /* kernels launched by this handle so far */
 
 /* ---- variables: tf.Variable init / assign / read (INF-L2:79-94, AB-ADMM:105-106) ---- */
@@ -129,7 +129,10 @@ int pinn_set_data_weight(pinn_handle_t h, float w);
  * TRAINING pass (pinn_loss_grad_device, pinn_adam_steps) stores its partial vector into every peer's slot, waits for
  * the peers' flags and leaves the SUM over ranks in the packed vector -- the one sum-allreduce of the step without a
  * separate collective -- and the fused Adam update applies to the summed gradient.  All ranks must run the same
- * sequence of training passes.  Fused path only (pinn_kernel_path == PINN_PATH_FUSED); world <= 8.            */
+ * sequence of training passes.  Fused path only (pinn_kernel_path == PINN_PATH_FUSED); world <= 8.  The data term
+ * must ride inside the fused pass (every loss but INF-L2's un-squared norm on shards above ~37 k points; the training
+ * entry points return PINN_E_STATE otherwise).  A peer that does not answer within 120 s makes the kernel drop the
+ * step (no Adam update) and raise a flag that every synchronising entry point reports as PINN_E_STATE.            */
 #define PINN_COMM_HANDLE_BYTES 64
 int pinn_comm_export(pinn_handle_t h, void* handle_out);
 int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles /* world x PINN_COMM_HANDLE_BYTES */);
@@ -150,6 +153,9 @@ int pinn_packed_ptr(pinn_handle_t h, float** dev_ptr);
 int pinn_l1_pass1(pinn_handle_t h, float** dev_sum_abs_f); /* V3 only: forward pass, local sum|f| */
 int pinn_loss_grad(pinn_handle_t h, double* loss, float* grad_host); /* grad_host: P (+2 if trainable_lambda) floats or NULL */
 int pinn_loss_value(pinn_handle_t h, double* loss);                   /* sess.run(self.loss)  INF-L2:138 */
+/* self.admm_misfit = mean|f_pred - z| (AB-ADMM:60, printed as "r(w) - z" at :232-233): the value the last
+ * pinn_loss_value pass accumulated on this handle's points (0 for the non-ADMM losses).                    */
+int pinn_admm_misfit(pinn_handle_t h, double* misfit);
 
 /* ---- train_op_Adam: tf.train.AdamOptimizer.minimize (INF-L2:72-73,:135) ----
  * pinn_adam_apply consumes the packed vector (after the caller's allreduce, if any).

@@ -18,7 +18,8 @@ PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_TENSOR = 0, 1, 2, 3
 NSUMS = 8
 SUM_DATA, SUM_RES, SUM_ABSF, SUM_MISFIT, SUM_F2 = 0, 1, 2, 3, 4
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_b200.so")
+# PINN_B200_LIB: measurement knob (A/B runs of differently compiled kernels); the default is the in-tree build
+LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpinn_b200.so")
 
 
 class PinnConfig(C.Structure):
@@ -73,6 +74,7 @@ PROTOTYPES = {
     "pinn_l1_pass1": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "pinn_loss_grad": (C.c_int, [_H, C.POINTER(C.c_double), C.c_void_p]),
     "pinn_loss_value": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "pinn_admm_misfit": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "pinn_adam_config": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float]),
     "pinn_adam_apply": (C.c_int, [_H]),
     "pinn_adam_steps": (C.c_int, [_H, C.c_int64]),

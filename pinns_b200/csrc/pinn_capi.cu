@@ -86,8 +86,16 @@ struct pinn_handle_s {
     size_t slot_bytes = 0;
     int rvlen_pad = 0, nchunks = 0;
     unsigned seq = 0;
-    int* d_hang = nullptr;
+    int* h_hang = nullptr;               // pinned, mapped: the reduction kernel raises it, every synchronising call reads it
+    int* d_hang = nullptr;               // device alias of h_hang
   } comm;
+
+  // staging buffers of pinn_predict for host callers (grown on demand, kept for the handle's lifetime)
+  double last_misfit = 0.0;  // mean |f - z| of the last pinn_loss_value pass (admm_misfit, AB-ADMM:60)
+  float* d_pred_X = nullptr;
+  float* d_pred_u = nullptr;
+  float* d_pred_f = nullptr;
+  int64_t pred_cap = 0;
 };
 
 static std::string g_create_err;
@@ -463,7 +471,10 @@ int pinn_destroy(pinn_handle_t h) {
   for (cudaEvent_t e : h->feed_ev) cudaEventDestroy(e);
   pinn_comm_detach(h);
   if (h->comm.own) cudaFree(h->comm.own);
-  if (h->comm.d_hang) cudaFree(h->comm.d_hang);
+  if (h->comm.h_hang) cudaFreeHost(h->comm.h_hang);
+  if (h->d_pred_X) cudaFree(h->d_pred_X);
+  if (h->d_pred_u) cudaFree(h->d_pred_u);
+  if (h->d_pred_f) cudaFree(h->d_pred_f);
   float* bufs[] = {h->d_theta, h->d_wp,   h->d_wt,   h->d_packed, h->d_Xu,      h->d_u,   h->d_upred,     h->d_seed,
                    h->d_Xf_owned, h->d_z, h->d_gamma, h->adam.m,  h->adam.v,    h->d_scratch, h->d_part, h->d_part_data,
                    h->d_l1sum, h->d_data_loss};
@@ -479,10 +490,22 @@ int pinn_set_stream(pinn_handle_t h, void* s) {
   return PINN_OK;
 }
 
+// after a stream synchronisation: did a kernel give up waiting (a lost data-parallel peer, a tcgen05 mbarrier that never
+// completed)?  Then the replicated state is no longer trustworthy and every synchronising entry point says so.
+static int check_device_flags(pinn_handle_t h) {
+  if (h->comm.h_hang && *(volatile int*)h->comm.h_hang) {
+    h->err = "peer-memory exchange: a peer's flag did not arrive within 120 s; the step was dropped (no Adam update), the job is out of sync";
+    return PINN_E_STATE;
+  }
+  if (h->tensor.enabled) return tensor_check_hang(h->tensor, h->stream, h->err);
+  return PINN_OK;
+}
+
 int pinn_synchronize(pinn_handle_t h) {
   if (!h) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
-  return PINN_OK;
+  return check_device_flags(h);
 }
 
 int pinn_num_params(pinn_handle_t h, int64_t* n) {
@@ -495,9 +518,16 @@ int pinn_packed_len(pinn_handle_t h, int64_t* n) {
   *n = h->rvlen;
   return PINN_OK;
 }
+static bool tensor_takes(const pinn_handle_s* h, int64_t n) {
+  return !h->fused.enabled && h->tensor.enabled && (h->tensor.forced || n >= TENSOR_MIN_POINTS);
+}
+
 int pinn_kernel_path(pinn_handle_t h, int32_t* p) {
   if (!h || !p) return PINN_E_INVALID;
-  *p = h->path_used;
+  // the path the CURRENT collocation batch takes (before any batch is set: the one a large batch would take)
+  if (h->fused.enabled) *p = PINN_PATH_FUSED;
+  else if (h->tensor.enabled && (h->n_f == 0 || tensor_takes(h, h->n_f))) *p = PINN_PATH_TENSOR;
+  else *p = PINN_PATH_GENERIC;
   return PINN_OK;
 }
 int pinn_launch_count(pinn_handle_t h, int64_t* n) {
@@ -521,7 +551,10 @@ int pinn_get_params(pinn_handle_t h, float* theta, int on_device) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(theta, h->d_theta, (size_t)h->net.P * sizeof(float),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-  if (!on_device) CK(cudaStreamSynchronize(h->stream));
+  if (!on_device) {
+    CK(cudaStreamSynchronize(h->stream));
+    return check_device_flags(h);
+  }
   return PINN_OK;
 }
 
@@ -548,22 +581,33 @@ int pinn_get_lambda(pinn_handle_t h, float* l1, float* l2) {
 int pinn_set_data(pinn_handle_t h, const float* X_u, const float* u, int64_t n_u, int on_device) {
   if (!h || n_u < 0 || (n_u > 0 && (!X_u || !u))) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));
+  // the new buffers are allocated and filled first: a failure leaves the previous data term in place
+  float* nb[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (n_u > 0) {
+    const size_t no = (size_t)h->net.n_out;
+    const size_t bytes[4] = {(size_t)n_u * 2 * sizeof(float), (size_t)n_u * no * sizeof(float), (size_t)n_u * no * sizeof(float),
+                             (size_t)n_u * no * sizeof(float)};
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaMalloc(&nb[k], bytes[k]);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nb[0], X_u, bytes[0], kind, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nb[1], u, bytes[1], kind, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      for (float* b : nb)
+        if (b) cudaFree(b);
+      h->err = std::string("pinn_set_data: ") + cudaGetErrorString(e);
+      return PINN_E_CUDA;
+    }
+  } else {
+    CK(cudaStreamSynchronize(h->stream));  // nothing in flight reads the buffers about to be freed
+  }
   float** bufs[] = {&h->d_Xu, &h->d_u, &h->d_upred, &h->d_seed};
-  for (float** b : bufs) {
-    if (*b) cudaFree(*b);
-    *b = nullptr;
+  for (int k = 0; k < 4; ++k) {
+    if (*bufs[k]) cudaFree(*bufs[k]);
+    *bufs[k] = nb[k];
   }
   h->n_u = n_u;
-  if (n_u == 0) return PINN_OK;
-  const size_t no = (size_t)h->net.n_out;
-  CK(cudaMalloc(&h->d_Xu, (size_t)n_u * 2 * sizeof(float)));
-  CK(cudaMalloc(&h->d_u, (size_t)n_u * no * sizeof(float)));
-  CK(cudaMalloc(&h->d_upred, (size_t)n_u * no * sizeof(float)));
-  CK(cudaMalloc(&h->d_seed, (size_t)n_u * no * sizeof(float)));
-  const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CK(cudaMemcpyAsync(h->d_Xu, X_u, (size_t)n_u * 2 * sizeof(float), k, h->stream));
-  CK(cudaMemcpyAsync(h->d_u, u, (size_t)n_u * no * sizeof(float), k, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   return PINN_OK;
 }
 
@@ -681,6 +725,7 @@ int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index
 int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device) {
   if (!h || !X_f) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_get_collocation: no collocation points set");
+  CK(cudaSetDevice(h->cfg.device));
   {
     int rc = feed_join(h);
     if (rc) return rc;
@@ -753,7 +798,7 @@ static bool fused_handles_data(const pinn_handle_s* h) {
 // same for the generic kernel's training pass (dual launch) when neither the fused nor the tensor kernel takes the batch
 static bool generic_handles_data(const pinn_handle_s* h) {
   if (h->fused.enabled) return false;
-  if (h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS)) return false;
+  if (tensor_takes(h, h->n_f)) return false;
   return h->cfg.loss != PINN_LOSS_V1_INF_L2 && h->n_u > 0 && h->data_weight != 0.0f;
 }
 
@@ -843,7 +888,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
   rc = feed_join(h);
   if (rc) return rc;
   int grid = 0;
-  if (h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS)) {
+  if (tensor_takes(h, h->n_f)) {
     if (h->tensor_dirty) {
       rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
       if (rc) return rc;
@@ -896,10 +941,14 @@ int pinn_loss_grad_device(pinn_handle_t h) {
     rc = pinn_l1_pass1(h, nullptr);
     if (rc) return rc;
   }
+  const bool data_inside = fused_handles_data(h) || generic_handles_data(h);
+  REQUIRE(!(h->comm.attached && h->comm.world > 1) || data_inside || h->n_u == 0 || h->data_weight == 0.0f, PINN_E_STATE,
+          "pinn_loss_grad_device: peer-memory exchange attached but the data term is not part of the fused pass (V1 loss on "
+          "a large shard): detach and combine the ranks with an allreduce of the packed vector instead");
   rc = residual_pass(h, GEN_MODE_TRAIN, 0);
   if (rc) return rc;
   h->l1_ready = false;
-  if (fused_handles_data(h) || generic_handles_data(h)) return PINN_OK;
+  if (data_inside) return PINN_OK;
   return data_term(h, true);
 }
 
@@ -930,10 +979,8 @@ int pinn_loss_grad(pinn_handle_t h, double* loss, float* grad_host) {
     CK(cudaMemcpyAsync(grad_host, h->d_packed, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
-  if (h->tensor.enabled) {
-    rc = tensor_check_hang(h->tensor, h->stream, h->err);
-    if (rc) return rc;
-  }
+  rc = check_device_flags(h);
+  if (rc) return rc;
   if (loss) *loss = assemble_loss(h, sums);
   return PINN_OK;
 }
@@ -951,7 +998,10 @@ int pinn_loss_value(pinn_handle_t h, double* loss) {
   CK(cudaMemcpyAsync(sums, h->d_packed + h->net.P + 2, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&dl, h->d_data_loss, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  rc = check_device_flags(h);
+  if (rc) return rc;
   sums[PINN_SUM_DATA] = dl;
+  h->last_misfit = (double)sums[PINN_SUM_MISFIT] / ((double)h->n_f * h->net.n_res);
   *loss = assemble_loss(h, sums);
   return PINN_OK;
 }
@@ -993,6 +1043,11 @@ int pinn_adam_steps(pinn_handle_t h, int64_t n_steps) {
   // single-GPU fast lane: when the fused kernel also carries the data term, a step is two launches
   // (residual+grad kernel, finalize+Adam) with no host round trip
   const bool lane2 = h->fused.enabled && (fused_handles_data(h) || h->n_u == 0 || h->data_weight == 0.0f);
+  // with a peer-memory group attached the exchange happens inside the reduction of the residual pass: a data term that
+  // is added afterwards (INF-L2's un-squared norm on a batch too large to carry it) would miss the sum over ranks
+  REQUIRE(!(h->comm.attached && h->comm.world > 1) || lane2, PINN_E_STATE,
+          "pinn_adam_steps: peer-memory exchange attached but the data term is not part of the fused pass (V1 loss on a "
+          "large shard): detach and combine the ranks with an allreduce of the packed vector instead");
   for (int64_t it = 0; it < n_steps; ++it) {
     int rc;
     if (lane2) {
@@ -1026,13 +1081,14 @@ int pinn_admm_adam_step(pinn_handle_t h, int quirk) {
   CK(cudaSetDevice(h->cfg.device));
   int rc = feed_join(h);
   if (rc) return rc;
-  const bool tensor = !h->fused.enabled && h->tensor.enabled && (h->tensor.forced || h->n_f >= TENSOR_MIN_POINTS);
-  if (tensor) {
+  if (tensor_takes(h, h->n_f)) {
     rc = pinn_admm_update(h, quirk);
     return rc ? rc : pinn_adam_steps(h, 1);
   }
   const bool lane2 = h->fused.enabled && (fused_handles_data(h) || h->n_u == 0 || h->data_weight == 0.0f);
   if (lane2) return residual_pass(h, GEN_MODE_TRAIN, op, /*fuse_adam=*/true);
+  REQUIRE(!(h->comm.attached && h->comm.world > 1), PINN_E_STATE,
+          "pinn_admm_adam_step: peer-memory exchange attached but the data term is not part of the fused pass");
   rc = residual_pass(h, GEN_MODE_TRAIN, op);
   if (rc) return rc;
   if (!(fused_handles_data(h) || generic_handles_data(h))) {
@@ -1047,27 +1103,27 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
   CK(cudaSetDevice(h->cfg.device));
   int rc = PINN_OK;
   const float* dX = X;
-  float *tX = nullptr, *tu = nullptr, *tf = nullptr;
   float *du = u_out, *df = f_out;
   const size_t no = h->net.n_out, nr = h->net.n_res;
-  auto cleanup = [&]() {
-    if (tX) cudaFree(tX);
-    if (tu) cudaFree(tu);
-    if (tf) cudaFree(tf);
-  };
   if (!on_device) {
-    cudaError_t e = cudaMalloc(&tX, (size_t)n * 2 * sizeof(float));
-    if (e == cudaSuccess && u_out) e = cudaMalloc(&tu, (size_t)n * no * sizeof(float));
-    if (e == cudaSuccess && f_out) e = cudaMalloc(&tf, (size_t)n * nr * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(tX, X, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) {
-      cleanup();
-      h->err = std::string("pinn_predict: ") + cudaGetErrorString(e);
-      return PINN_E_CUDA;
+    // staging buffers live in the handle: record_data calls this every 100 / 1000 epochs (AB-ADMM:238-246)
+    if (n > h->pred_cap) {
+      CK(cudaStreamSynchronize(h->stream));
+      float** bufs[] = {&h->d_pred_X, &h->d_pred_u, &h->d_pred_f};
+      for (float** b : bufs) {
+        if (*b) cudaFree(*b);
+        *b = nullptr;
+      }
+      h->pred_cap = 0;
+      CK(cudaMalloc(&h->d_pred_X, (size_t)n * 2 * sizeof(float)));
+      CK(cudaMalloc(&h->d_pred_u, (size_t)n * no * sizeof(float)));
+      CK(cudaMalloc(&h->d_pred_f, (size_t)n * nr * sizeof(float)));
+      h->pred_cap = n;
     }
-    dX = tX;
-    du = tu;
-    df = tf;
+    CK(cudaMemcpyAsync(h->d_pred_X, X, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    dX = h->d_pred_X;
+    du = u_out ? h->d_pred_u : nullptr;
+    df = f_out ? h->d_pred_f : nullptr;
   }
   if (h->fused.enabled) {
     // forward-only mode of the fused kernel: u and f of every point in one pass (INF-L2:143-148 does two sess.runs)
@@ -1076,7 +1132,7 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
     rc = fused_run(h->fused, h->net, lc, h->d_theta, dX, n, n, GEN_MODE_FORWARD, nullptr, nullptr, nullptr, 0, du, df, nullptr,
                    nullptr, 0, 0.f, nullptr, none, nullptr, nullptr, h->stream, h->err);
     h->launches += 1;
-  } else if (h->tensor.enabled && f_out && (h->tensor.forced || n >= TENSOR_MIN_POINTS)) {
+  } else if (f_out && tensor_takes(h, n)) {
     if (h->tensor_dirty) {
       rc = tensor_prep(h->tensor, h->d_theta, h->stream, h->err);
       h->tensor_dirty = false;
@@ -1091,17 +1147,18 @@ int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float
     rc = run_generic(h, 1, GEN_MODE_FORWARD, PINN_LOSS_V4_MSE, dX, n, nullptr, du, nullptr, 0, false, h->d_part_data, nullptr);
   }
   if (rc == PINN_OK && !on_device) {
-    cudaError_t e = cudaSuccess;
-    if (u_out) e = cudaMemcpyAsync(u_out, tu, (size_t)n * no * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess && f_out) e = cudaMemcpyAsync(f_out, tf, (size_t)n * nr * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) {
-      h->err = std::string("pinn_predict: ") + cudaGetErrorString(e);
-      rc = PINN_E_CUDA;
-    }
+    if (u_out) CK(cudaMemcpyAsync(u_out, du, (size_t)n * no * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (f_out) CK(cudaMemcpyAsync(f_out, df, (size_t)n * nr * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = check_device_flags(h);
   }
-  cleanup();
   return rc;
+}
+
+int pinn_admm_misfit(pinn_handle_t h, double* misfit) {
+  if (!h || !misfit) return PINN_E_INVALID;
+  *misfit = h->last_misfit;
+  return PINN_OK;
 }
 
 int pinn_admm_init(pinn_handle_t h) {
@@ -1127,6 +1184,7 @@ int pinn_admm_update(pinn_handle_t h, int quirk) {
 int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device) {
   if (!h) return PINN_E_INVALID;
   REQUIRE(h->d_z && h->n_f > 0, PINN_E_STATE, "pinn_admm_get_state: ADMM state not initialised");
+  CK(cudaSetDevice(h->cfg.device));
   const size_t bytes = (size_t)h->n_f * h->net.n_res * sizeof(float);
   const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (z) CK(cudaMemcpyAsync(z, h->d_z, bytes, k, h->stream));
@@ -1161,8 +1219,9 @@ int pinn_comm_export(pinn_handle_t h, void* handle_out) {
     const size_t bytes = h->comm.slot_bytes + (size_t)2 * PINN_MAX_RANKS * h->comm.nchunks * sizeof(unsigned);
     CK(cudaMalloc(&h->comm.own, bytes));
     CK(cudaMemset(h->comm.own, 0, bytes));
-    CK(cudaMalloc(&h->comm.d_hang, sizeof(int)));
-    CK(cudaMemset(h->comm.d_hang, 0, sizeof(int)));
+    CK(cudaHostAlloc(&h->comm.h_hang, sizeof(int), cudaHostAllocMapped));
+    *h->comm.h_hang = 0;
+    CK(cudaHostGetDevicePointer(&h->comm.d_hang, h->comm.h_hang, 0));
     CK(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t ipc;
@@ -1182,13 +1241,19 @@ int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles) 
     if (r == rank) continue;
     cudaIpcMemHandle_t ipc;
     memcpy(&ipc, hs + (size_t)r * PINN_COMM_HANDLE_BYTES, sizeof(ipc));
-    CK(cudaIpcOpenMemHandle(&h->comm.opened[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&h->comm.opened[r], ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // leave nothing mapped behind: the caller falls back to the allreduce
+      h->comm.opened[r] = nullptr;
+      pinn_comm_detach(h);
+      h->err = std::string("pinn_comm_attach: cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+      return PINN_E_CUDA;
+    }
   }
   // a fresh numbering of the exchanges needs fresh flags (the peers store into this buffer only after the caller's
   // barrier that follows the attach)
   CK(cudaMemset(h->comm.own, 0, h->comm.slot_bytes + (size_t)2 * PINN_MAX_RANKS * h->comm.nchunks * sizeof(unsigned)));
-  CK(cudaMemset(h->comm.d_hang, 0, sizeof(int)));
   CK(cudaDeviceSynchronize());
+  *h->comm.h_hang = 0;
   h->comm.rank = rank;
   h->comm.world = world;
   h->comm.seq = 0;
@@ -1199,7 +1264,7 @@ int pinn_comm_attach(pinn_handle_t h, int rank, int world, const void* handles) 
 int pinn_comm_detach(pinn_handle_t h) {
   if (!h) return PINN_E_INVALID;
   cudaSetDevice(h->cfg.device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->stream);  // (the legacy default stream is a valid argument) no exchange kernel may still be running
   for (int r = 0; r < PINN_MAX_RANKS; ++r)
     if (h->comm.opened[r]) {
       cudaIpcCloseMemHandle(h->comm.opened[r]);
@@ -1214,11 +1279,10 @@ int pinn_comm_status(pinn_handle_t h, int32_t* attached, int32_t* hang) {
   if (attached) *attached = h->comm.attached ? 1 : 0;
   if (hang) {
     *hang = 0;
-    if (h->comm.d_hang) {
-      int v = 0;
-      CK(cudaMemcpyAsync(&v, h->comm.d_hang, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->comm.h_hang) {
+      CK(cudaSetDevice(h->cfg.device));
       CK(cudaStreamSynchronize(h->stream));
-      *hang = v;
+      *hang = *(volatile int*)h->comm.h_hang;
     }
   }
   return PINN_OK;
@@ -1233,6 +1297,7 @@ int pinn_kernel_timing(pinn_handle_t h, int enable) {
 
 int pinn_kernel_time(pinn_handle_t h, double* total_ms, int64_t* n_launches) {
   if (!h || !total_ms) return PINN_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   double tot = 0.0;
   for (size_t k = 0; k + 1 < h->ev_used; k += 2) {

@@ -39,9 +39,13 @@ def allreduce_sum_(tensor, group=None):
 def attach_peer_memory(engine, rank: int, world: int, group=None) -> bool:
     """Gathers the engines' CUDA IPC handles over the process group and joins them into one peer-memory exchange group.
     Returns False (and changes nothing) when the engine is not on the fused path, the job has one rank or more than
-    eight, or the L1^2 loss needs its scalar allreduce between two passes."""
+    eight, the L1^2 loss needs its scalar allreduce between two passes, or the loss is INF-L2's un-squared data norm
+    (V1): its data gradient joins the packed vector AFTER the reduction kernel whenever rank 0's shard is too large to
+    carry the data batches in warps of their own, i.e. after the in-kernel exchange -- the allreduce route sums the
+    finished vector instead (the C ABI refuses the combination too: PINN_E_STATE)."""
     import torch.distributed as dist
     ok = (world > 1 and world <= 8 and engine.kernel_path == "fused" and not eng_loss_is_l1(engine)
+          and getattr(engine, "loss_kind", "") not in ("v1", "v1_inf_l2")
           and dist.is_available() and dist.is_initialized())
     if not ok:
         return False
@@ -59,6 +63,10 @@ def attach_peer_memory(engine, rank: int, world: int, group=None) -> bool:
             engine.comm_attach(rank, world, handles)
         except Exception:
             good = False
+            try:
+                engine.comm_detach()   # close whatever was mapped before the failure
+            except Exception:
+                pass
     votes = [None] * world
     dist.all_gather_object(votes, good, group=group)
     if not all(votes):
@@ -67,6 +75,16 @@ def attach_peer_memory(engine, rank: int, world: int, group=None) -> bool:
         return False
     dist.barrier(group=group)          # every rank has mapped its peers before anybody stores into them
     return True
+
+
+def detach_peer_memory(engine, group=None) -> None:
+    """Leaves the exchange group in the order CUDA IPC asks for: every rank unmaps its peers' buffers, and only after
+    a barrier may anybody free (close) the buffer it exported."""
+    import torch.distributed as dist
+    if getattr(engine, "comm_attached", False):
+        engine.comm_detach()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)
 
 
 class DataParallelStepper:
@@ -79,6 +97,12 @@ class DataParallelStepper:
         self._packed = engine.packed_tensor() if world > 1 else None
         self._l1 = None
         self.peer_memory = bool(peer_memory) and attach_peer_memory(engine, rank, world, group)
+
+    def close(self):
+        """Call on every rank before the engine is destroyed (see detach_peer_memory)."""
+        if self.world > 1:
+            detach_peer_memory(self.engine, self.group)
+        self.peer_memory = False
 
     def loss_grad_device(self):
         eng = self.engine
@@ -93,8 +117,10 @@ class DataParallelStepper:
             allreduce_sum_(self._packed, self.group)
 
     def adam_step(self):
-        if self.peer_memory:
-            self.engine.adam_steps(1)  # residual+grad kernel, then ONE kernel: reduction + exchange + Adam
+        if self.peer_memory or self.world == 1:
+            # residual+grad kernel, then ONE kernel: reduction (+ exchange over NVLink) + Adam -- the same two-launch
+            # route on one GPU and on eight
+            self.engine.adam_steps(1)
             return
         self.loss_grad_device()
         self.engine.adam_apply()

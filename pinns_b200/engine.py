@@ -261,6 +261,12 @@ class Engine:
         self._ck(capi.lib.pinn_loss_value(self._h, C.byref(loss)), "pinn_loss_value")
         return float(loss.value)
 
+    def admm_misfit(self) -> float:
+        """mean |f - z| of the last loss_value() pass: the reference's `admm_misfit` (AB-ADMM:60, "r(w) - z" at :232)."""
+        v = C.c_double()
+        self._ck(capi.lib.pinn_admm_misfit(self._h, C.byref(v)), "pinn_admm_misfit")
+        return float(v.value)
+
     def loss_from_packed(self, sums, nf_global: int, loss_kind: str) -> float:
         """Assemble the scalar loss from the (all-reduced) partial sums of the packed vector."""
         s = [float(v) for v in sums]

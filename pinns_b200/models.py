@@ -431,7 +431,11 @@ class BurgersIdentification(_Base):
                 elapsed = time.time() - start_time
                 loss_value = self.engine.loss_value()
                 if self.verbose:
-                    print('It: %d, Loss: %.3e, Time: %.2f' % (epoch, loss_value, elapsed))
+                    if self._admm:                                            # AB-ADMM:231-234 prints admm_misfit too
+                        self.r_z = self.engine.admm_misfit()
+                        print('It: %d, Loss: %.3e, r(w) - z: %.3f ,Time: %.2f' % (epoch, loss_value, self.r_z, elapsed))
+                    else:
+                        print('It: %d, Loss: %.3e, Time: %.2f' % (epoch, loss_value, elapsed))
                 start_time = time.time()
             if self._record and epoch % every == 0:
                 self.record_data(epoch)

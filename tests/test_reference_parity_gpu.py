@@ -33,24 +33,63 @@ def test_loss_gradient_residuals_against_the_reference_graph(name):
     loss, grad = eng.loss_grad()
     P = eng.num_params
     assert abs(loss - fx["vec_loss"]) <= TOL * abs(fx["vec_loss"]), (loss, fx["vec_loss"])
-    err = float(np.linalg.norm(grad[:P] - fx["vec_grad"]))
-    scale = float(np.linalg.norm(fx["vec_grad"]))
+    err = float(np.linalg.norm(grad[:P] - fx["vec_grad"])) / float(np.linalg.norm(fx["vec_grad"]))
+    bound = TOL
     if "vec_z" in fx and name != "INF-ADMM":
-        # The scripts evaluate this gradient right after the z/gamma update on the same batch (AB-ADMM:225-226), where
-        # the adjoint seed rho*(f - z) + gamma collapses to +-1/N_f: three to four digits of f cancel, and a float32
-        # evaluation of the reference graph itself misses this vector by 8e-6 (ID-ADMMb) ... 1e-3 (EUL).  The error is
-        # therefore bounded against what is being cancelled -- the gradient of the bare penalty (rho/2)||f||^2 -- at a
-        # tenth of the fp32 budget.
-        zero = np.zeros_like(fx["vec_z"])
-        bare = tg.evaluate(np.float32(fx["stage%d_theta" % _last_stage(fx)]), p, fx["X_u"], fx["u_data"], fx["vec_X_f"],
-                           z=zero, gamma=zero)
-        scale = max(scale, 0.1 * float(np.linalg.norm(bare.grad)))
-    print("%s: gradient error %.2e of |g|, %.2e of the bound's scale" % (name, err / np.linalg.norm(fx["vec_grad"]), err / scale))
-    assert err <= TOL * scale, (err, scale)
+        # The scripts evaluate this gradient right after the z/gamma update on the same batch (AB-ADMM:225-226,
+        # Burgers_ADMM_batch.py:204-210), where the adjoint seed rho*(f - z) + gamma collapses to +-1/N_f: three to four
+        # digits of f cancel and ANY float32 evaluation misses the float64 vector by 1e-5 ... 1e-3 of |g| -- the reference's
+        # own graph evaluated in float32 included.  That evaluation is made here, on the same state, and the CUDA path is
+        # held to three times its error (test_admm_cancellation_states_* below looks at a distribution of such states).
+        import torch
+        g32 = tg.evaluate(np.float32(fx["stage%d_theta" % _last_stage(fx)]), p, fx["X_u"], fx["u_data"], fx["vec_X_f"],
+                          z=fx["vec_z"], gamma=fx["vec_gamma"], dtype=torch.float32).grad
+        err32 = float(np.linalg.norm(g32 - fx["vec_grad"]) / np.linalg.norm(fx["vec_grad"]))
+        bound = max(TOL, 3.0 * err32)
+        print("%s: float32 evaluation of the reference graph: gradient error %.2e of |g|" % (name, err32))
+    print("%s: CUDA path: gradient error %.2e of |g| (bound %.2e)" % (name, err, bound))
+    assert err <= bound, (err, bound)
     y, f = eng.predict(fx["vec_X_f"])
     assert max_rel_err(f, fx["vec_f"]) <= TOL
     y_u, _ = eng.predict(fx["X_u"], want_f=False)
     assert max_rel_err(y_u, fx["vec_u_pred"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["ID-ADMMb", "AB-ADMM"])
+def test_admm_cancellation_states_error_distribution(name):
+    """The cancellation regime as a distribution instead of one draw: eight fresh batches from the fixture's parameters,
+    z/gamma updated from float64 residuals and rounded to float32 like the reference's variables, float64 gradient =
+    truth.  The fused kernel's median error stays within 3x of the median error of a float32 evaluation of the reference
+    graph on the same states (measured: 5.0e-5 against 2.6e-5 on ID-ADMMb, 1.2e-5 against 5.5e-6 on AB-ADMM; round 1's
+    exponential-only tanh: 2.5e-4 / 4.0e-5)."""
+    import torch
+    from pinns_b200 import Engine
+    fx = load_ref_fixture(name)
+    p = ref_problem(name, fx)
+    theta = np.float32(fx["stage%d_theta" % _last_stage(fx)])
+    n_f = fx["vec_X_f"].shape[0]
+    rng = np.random.default_rng(77)
+    z, gamma = fx["vec_z"].astype(np.float64), fx["vec_gamma"].astype(np.float64)
+    eng = Engine(p.layers, p.lb, p.ub, pde=p.pde, loss=ENGINE_LOSS[p.loss], lambda1=p.lam1, lambda2=p.lam2, rho=p.rho)
+    eng.set_params(theta)
+    eng.set_data(fx["X_u"], fx["u_data"])
+    e_gpu, e_32 = [], []
+    for _ in range(8):
+        X_f = p.lb + (p.ub - p.lb) * rng.random((n_f, 2))
+        f = tg.evaluate(theta, p, fx["X_u"], fx["u_data"], X_f, z=z, gamma=gamma, want_grad=False).f
+        z2, g2 = tg.admm_update(f, z, gamma, p.rho, n_f)
+        z2, g2 = z2.astype(np.float32), g2.astype(np.float32)
+        ref = tg.evaluate(theta, p, fx["X_u"], fx["u_data"], X_f, z=z2, gamma=g2).grad
+        g32 = tg.evaluate(theta, p, fx["X_u"], fx["u_data"], X_f, z=z2, gamma=g2, dtype=torch.float32).grad
+        eng.set_collocation(X_f)
+        eng.admm_set_state(z2, g2)
+        _, g = eng.loss_grad()
+        e_gpu.append(rel_err(g[:eng.num_params], ref))
+        e_32.append(rel_err(g32, ref))
+    print("%s: gradient error / |g| over 8 cancellation states: CUDA median %.2e (max %.2e), float32 reference graph median %.2e (max %.2e)"
+          % (name, np.median(e_gpu), max(e_gpu), np.median(e_32), max(e_32)))
+    assert np.median(e_gpu) <= 3.0 * np.median(e_32), (e_gpu, e_32)
+    assert max(e_gpu) <= 2e-4
 
 
 def _check_stage(fx, k, theta, z, gamma, pred, errors):

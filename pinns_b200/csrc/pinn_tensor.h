@@ -14,6 +14,9 @@ struct TensorState {
   float* d_wcan = nullptr;   // canonical hi/lo TF32 weight planes
   float* d_part = nullptr;   // [grid][rvlen]
   int* d_hang = nullptr;     // set by the kernel if an mbarrier wait times out
+  void* d_units = nullptr;   // the tile schedule (contraction units / worker items), built once per shape
+  void* d_items = nullptr;
+  int nu_f = 0, nu = 0, ni_f = 0, ni = 0;
 };
 
 // AUTO uses the tensor kernel from this many points on: below it the job has fewer 128-point tiles than the GPU has SMs

@@ -17,13 +17,19 @@ lib.pinn_tc_debug_trace(buf, C.byref(cnt))
 eng.loss_grad_device()
 lib.pinn_tc_debug_trace(buf, C.byref(cnt))
 ev = [(buf[2 * i], buf[2 * i + 1]) for i in range(cnt.value)]
-names = {1: 'tile start', 2: 'layer 0', 3: 'head+residual', 4: 'head reverse'}
+names = {1: "tile start (prev tile layer-0 reverse)", 2: "layer 0", 3: "head+residual", 4: "head reverse"}
 def name(t):
     if t in names: return names[t]
     if t >= 100: return 'fine %d' % t
     k, l = divmod(t, 10)
-    return {1: 'F contract', 2: 'F epilogue', 3: 'bias sums', 4: 'G contract', 5: 'G flush', 6: 'B contract', 7: 'B epilogue'}[k] + ' l=%d' % l
+    return {1: 'F wait for MMAs', 2: 'F epilogue', 3: 'bias sums', 4: 'G wait for MMAs', 5: 'G flush', 6: 'B wait for MMAs', 7: 'B epilogue'}[k] + ' l=%d' % l
 agg = collections.OrderedDict(); prev = None; tiles = 0
+vals = collections.OrderedDict()
+for tag, t in ev:
+    if tag >= 200:
+        vals.setdefault(tag, []).append(t)
+ev = [e for e in ev if e[0] < 200]
+ev.sort(key=lambda e: e[1])
 for tag, t in ev:
     if tag == 1: tiles += 1
     if tag >= 100: continue
@@ -43,3 +49,17 @@ if any(tag >= 100 for tag, _ in ev):
     t0 = ev[0][1]; p = t0
     for tag, t in ev[:int(sys.argv[4]) if len(sys.argv) > 4 else 400]:
         print('%4d t=%9d (+%7d)' % (tag, t - t0, t - p)); p = t
+
+vnames = {}
+for k, nm in ((0, 'F'), (1, 'B'), (2, 'G')):
+    vnames[200 + 10 * k] = nm + ' unit: issuer waited for the unit to begin'
+    vnames[201 + 10 * k] = nm + ' unit: issuer waited for staged operands'
+    vnames[202 + 10 * k] = nm + ' unit: issue span'
+vnames[230] = 'G unit: splitter waited for the TMA copies'
+vnames[231] = 'G unit: splitter spent splitting'
+vnames[240] = 'F unit: splitter waited for TMA (stages 1..)'
+vnames[241] = 'F unit: splitter spent splitting'
+vnames[232] = 'G unit: splitter in fence.proxy.async'
+for tag in sorted(vals):
+    v = vals[tag]
+    print('  %-48s mean %8.0f clk per unit (%d units)' % (vnames.get(tag, str(tag)), sum(v) / len(v), len(v)))

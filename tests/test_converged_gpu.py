@@ -1,0 +1,129 @@
+"""Converged accuracy of BASELINE configs 1-3 on the GPU against the oracle-trained finals (north_star: "final relative L2
+error versus the Data/ exact solutions within 10 % of the reference's").
+
+tests/golden/converged_<config>.json (made by tests/golden/make_converged.py) holds, per config, an ENSEMBLE of runs of
+the oracle's float32 evaluation of the reference graph -- the arithmetic TensorFlow itself uses -- started from
+theta0 * (1 + 1e-7 N(0,1)) (seed 0 = unperturbed), plus one float64 run.  The end point of a training run is a chaotic
+function of rounding, so "the reference's final error" is that ensemble, not one number:
+  * Euler (Adam only, 2999 epochs with per-epoch resampling, ADMM and MSE losses) spreads by 1-3 % over the ensemble: the
+    GPU runs (same schedules, same seeds, same NumPy RNG stream for the batches) must land within 10 % of the float32
+    ensemble MEAN, metric by metric;
+  * the L-BFGS-B configs (1: Adam then up to 15 000 iterations; 2: identification) end wherever float32 noise stops the line
+    search: config 1 float64 4.3e-4, float32 4.4e-3 ... 6.6e-3.  There the GPU runs may be at most 10 % worse than the worst
+    float32 oracle run (and are not faulted for ending closer to the float64 run).
+The measured values are printed (pytest -s) and kept in profiles/r02_converged_gpu.log.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tf_graph as tg
+from tests.golden.make_converged import converged_schedule, perturbed
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def ensemble(which, dtype="float32"):
+    path = os.path.join(GOLD, "converged_%s.json" % which)
+    if not os.path.exists(path):
+        pytest.skip("no oracle ensemble for %s" % which)
+    runs = [r for r in json.load(open(path)) if r["oracle_dtype"] == dtype]
+    if not runs:
+        pytest.skip("no %s oracle runs for %s" % (dtype, which))
+    return runs
+
+
+def report(which, metric, gpu, ref32, ref64):
+    print("%s %-10s GPU %s | float32 oracle ensemble %s (mean %.4e) | float64 oracle %s"
+          % (which, metric, ["%.4e" % v for v in gpu], ["%.4e" % v for v in ref32], float(np.mean(ref32)),
+             ["%.4e" % v for v in ref64]))
+
+
+@pytest.mark.parametrize("which", ["euler_admm", "euler_mse"])
+def test_euler_converged_errors_match_the_oracle_ensemble(which):
+    """BASELINE config 3: [2,200x5,3], N_data = 200, N_f = 1000 re-drawn every epoch, pen = 40, train(3000)
+    (Euler_ADMM.py:217-258,:342-347)."""
+    from pinns_b200.models import EulerInference, EulerParameters
+    ref32 = ensemble(which)
+    ref64 = json.load(open(os.path.join(GOLD, "converged_%s.json" % which)))
+    ref64 = [r for r in ref64 if r["oracle_dtype"] == "float64"]
+    g, layers, theta0, prob, sched = converged_schedule(which)
+    out = []
+    for seed in sorted(r["perturb_seed"] for r in ref32)[:2]:
+        class P(EulerParameters):
+            N_data = 200; N_f = 1000; pen = 40.0; epochs = sched["epochs"]; gpu = '0'
+        m = EulerInference(P(), data=os.path.join(GOLD, "data", "Abgrall_eulers.npz"), theta0=perturbed(theta0, seed),
+                           loss="v5" if which == "euler_admm" else "v4", verbose=False)
+        out.append({"error_rho": m.error_rho, "error_u": m.error_u, "error_E": m.error_E})
+    for metric in ("error_rho", "error_u", "error_E"):
+        gpu = [o[metric] for o in out]
+        r32 = [r[metric] for r in ref32]
+        report(which, metric, gpu, r32, [r[metric] for r in ref64])
+        mean32 = float(np.mean(r32))
+        for v in gpu:
+            assert abs(v - mean32) <= 0.10 * mean32, (which, metric, v, mean32)
+
+
+def test_identification_converged_errors_match_the_oracle_ensemble():
+    """BASELINE config 2: trainable (lambda1, lambda2) from (0, 0.0031831), N_u = 2000 interior samples, N_f = 2000, 2000 Adam
+    steps then L-BFGS-B over (theta, lambda) (Abgrall_L2.py:59-60 loss; Abgrall_ADMM.py:66-72 optimiser interface)."""
+    from pinns_b200 import Engine
+    from pinns_b200.models import PhysicsInformedNN
+    ref32 = ensemble("identification")
+    allruns = json.load(open(os.path.join(GOLD, "converged_identification.json")))
+    ref64 = [r for r in allruns if r["oracle_dtype"] == "float64"]
+    g, layers, theta0, prob, sched = converged_schedule("identification")
+    out = []
+    for seed in sorted(r["perturb_seed"] for r in ref32)[:3]:
+        eng = Engine(layers, prob.lb, prob.ub, pde="burgers", loss="v4", lambda1=prob.lam1, lambda2=prob.lam2, trainable_lambda=True)
+        eng.set_params(perturbed(theta0, seed))
+        eng.set_data(g["X_u"], g["u"])
+        eng.set_collocation(g["X_f"])
+        eng.adam_config(lr=1e-3)
+        eng.adam_steps(sched["adam_steps"])
+        m = PhysicsInformedNN.__new__(PhysicsInformedNN)   # the class surface (lbfgs_minimize) over this engine
+        m.engine, m.layers = eng, layers
+        res = m.lbfgs_minimize(sched["lbfgs"])
+        pred, _ = eng.predict(g["X_star"], want_f=False)
+        l1, l2 = eng.get_lambda()
+        out.append({"error_u": tg.relative_l2(g["u_star"], pred), "lambda1": l1, "lambda2": l2, "loss_final": float(res.fun)})
+    for metric in ("error_u", "lambda1", "lambda2"):
+        gpu = [o[metric] for o in out]
+        r32 = [r[metric] for r in ref32]
+        report("identification", metric, gpu, r32, [r[metric] for r in ref64])
+    # L-BFGS-B in float32 stops where rounding noise defeats the line search (2400 ... 3700 iterations in the oracle runs,
+    # 10 000 in float64): the end point scatters.  The GPU runs may not be more than 10 % WORSE than the float32 ensemble's
+    # worst run; ending closer to the float64 run (whose error is the floor) is not a failure.
+    r32 = [r["error_u"] for r in ref32]
+    floor64 = min([r["error_u"] for r in ref64] + r32)
+    for o in out:
+        assert 0.5 * floor64 <= o["error_u"] <= 1.1 * max(r32), (o["error_u"], r32, floor64)
+    for o in out:   # the identified coefficients: lambda1 -> 1, lambda2 -> 0.01/pi, as close as the float32 oracle gets
+        assert abs(o["lambda1"] - 1.0) <= 1.1 * max(abs(r["lambda1"] - 1.0) for r in ref32)
+        assert abs(o["lambda2"] - 0.01 / np.pi) <= 1.1 * max(abs(r["lambda2"] - 0.01 / np.pi) for r in ref32)
+
+
+def test_inference_converged_error_falls_inside_the_oracle_ensemble():
+    """BASELINE config 1 at full size (N_u = 100, N_f = 10 456, [2,20x8,1], nu = 0.01/pi, 2000 Adam steps then L-BFGS-B with the
+    reference's options, Abgrall_L2.py:68-72)."""
+    from pinns_b200.models import PhysicsInformedNN
+    ref32 = ensemble("inference")
+    old = os.path.join(GOLD, "e2e_burgers_inference_full_fp32.json")   # round 1's float32 run (Adam moments kept in float64)
+    r32 = [r["error_u"] for r in ref32] + ([json.load(open(old))["error_u_final"]] if os.path.exists(old) else [])
+    r64 = [json.load(open(os.path.join(GOLD, "e2e_burgers_inference_full.json")))["error_u_final"]]
+    g, layers, theta0, prob, sched = converged_schedule("inference")
+    gpu = []
+    for seed in (0, 1, 2):
+        m = PhysicsInformedNN(g["X_u"], g["u"], g["X_f"], layers, g["lb"], g["ub"], 0.01 / np.pi, '0', theta0=perturbed(theta0, seed),
+                              loss="v4", verbose=False)
+        m.engine.adam_steps(sched["adam_steps"])
+        m.lbfgs_minimize(sched["lbfgs"])
+        u, _ = m.predict(g["X_star"])
+        gpu.append(tg.relative_l2(g["u_star"], u))
+    report("inference", "error_u", gpu, r32, r64)
+    for v in gpu:   # not more than 10 % worse than the float32 ensemble's worst run, not below half of the float64 run's error
+        assert 0.5 * min(r64) <= v <= 1.1 * max(r32), (v, r32, r64)
+    assert max(gpu) <= 1e-2   # all runs are in the converged regime (the Adam-only error is 0.47)

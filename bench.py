@@ -223,8 +223,10 @@ def extra_config(torch, dev_index, name, layers, pde, loss, n_u, n_f, steps, fpp
     k_ms, k_n = eng.kernel_time()
     eng.kernel_timing(False)
     kpath = eng.kernel_path
-    kname = {"fused": "pinn_fused_kernel<20,true>", "generic": "pinn_generic_kernel<%d>" % (4 if pde == "burgers" else 3),
-             "tensor": "pinn_tc_kernel (tcgen05, 3xTF32)"}[kpath]
+    small = kpath == "fused" and (n_f + 7) // 8 + (n_u + 7) // 8 <= 148 * 8   # one 8-point batch per warp: four lanes per point
+    kname = {"fused": "pinn_fused_small_kernel<20,true>" if small else "pinn_fused_kernel<20,true>",
+             "generic": "pinn_generic_kernel<%d>" % (4 if pde == "burgers" else 3),
+             "tensor": "pinn_tc_kernel<%s> (tcgen05 + TMA, 3xTF32)" % ("4,1" if pde == "burgers" else "3,3")}[kpath]
     tflops = n_f * fpp / (ms * 1e-3) / 1e12
     out = {"workload": name, "layers": "[2,%dx%d,%d]" % (layers[1], len(layers) - 2, layers[-1]), "loss": loss, "n_f": n_f,
            "n_u": n_u, "ms_per_step": ms, "points_per_s": n_f / (ms * 1e-3), "steps": steps, "launches_per_step": launches / steps,
@@ -449,7 +451,7 @@ def run_ours(args, rank, world, local_rank):
         extra["config5_wide128_16Mi"] = {
             "workload": "BASELINE config 5: layers [2,128x8,1], N_f=%d global (strong), MSE loss + Adam" % g5,
             "n_gpus": world, "nf_per_gpu": n5, "ms_per_step": ms5, "points_per_s": g5 / (ms5 * 1e-3), "steps": 3,
-            "kernel_path": e5.kernel_path, "kernel": "pinn_tc_kernel (tcgen05, 3xTF32)", "kernel_ms": k5_ms / max(k5_n, 1),
+            "kernel_path": e5.kernel_path, "kernel": "pinn_tc_kernel<4,1> (tcgen05 + TMA, 3xTF32)", "kernel_ms": k5_ms / max(k5_n, 1),
             "rank_sum": "one NCCL allreduce of the packed vector (464 KB)" if world > 1 else "single GPU",
             "algorithmic_tflops": tfl, "tensor_tflops_issued": 3 * tfl, "frac_tf32_peak": 3 * tfl / (tf32_peak() * world),
             "frac_fp32_peak": tfl / (peak_meas * world), "tf32_peak_per_gpu": tf32_peak()}
@@ -467,11 +469,18 @@ def run_ours(args, rank, world, local_rank):
             extra["config3_euler_1000"] = extra_config(torch, local_rank, "BASELINE config 3: Euler ADMM step, 1000 + 200 points", EUL,
                                                        "euler", "v5", 200, 1000, 50, F_POINT_EULER, peak_meas,
                                                        ref="Euler_ADMM.py:128-133,:217-258")
-            extra["config3_euler_65536"] = extra_config(torch, local_rank, "Euler [2,200x5,3] at 65 536 points", EUL, "euler", "v5",
-                                                        200, 65536, 5, F_POINT_EULER, peak_meas, ref="Euler_ADMM.py:176-198")
+            extra["identification_batch_5000"] = extra_config(torch, local_rank, "ID-ADMMb batch: 5000 + 100 points, ADMM loss", LAYERS,
+                                                              "burgers", "v5", 100, 5000, 200, F_POINT, peak_meas,
+                                                              ref="Burgers_ADMM_batch.py:118-119,:29-34")
+            extra["config3_euler_65536"] = extra_config(torch, local_rank, "Euler [2,200x5,3] at 65 536 points (tensor path from 8192 points on)",
+                                                        EUL, "euler", "v5", 200, 65536, 5, F_POINT_EULER, peak_meas, ref="Euler_ADMM.py:176-198")
+            extra["config3_euler_65536_generic"] = extra_config(torch, local_rank, "the same on the FP32 generic kernel", EUL, "euler", "v5",
+                                                                200, 65536, 3, F_POINT_EULER, peak_meas, path="generic", ref="Euler_ADMM.py:176-198")
             extra["abgrall_l2_wide200_1000"] = extra_config(torch, local_rank, "AB-L2 batch: [2,200x8,1], 1000 + 100 points", B200x8,
                                                             "burgers", "v4", 100, 1000, 50, 6731200.0, peak_meas,
                                                             ref="Abgrall_L2.py:59-60,:247")
+            extra["abgrall_l2_wide200_262144"] = extra_config(torch, local_rank, "[2,200x8,1] at 262 144 points (tensor path)", B200x8,
+                                                              "burgers", "v4", 100, 262144, 3, 6731200.0, peak_meas, ref="Abgrall_L2.py:247")
             extra["config5_wide128_262144"] = extra_config(torch, local_rank, "BASELINE config 5 net at 262 144 points", W128, "burgers",
                                                            "v4", 100, 262144, 5, F_POINT_W128, peak_meas, ref="north_star config 5")
     if rank != 0:

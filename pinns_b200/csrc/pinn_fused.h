@@ -43,6 +43,9 @@ struct FusedState {
   int discard = 0;            // discard.global.L2 on stash lines after their last read: dead data is not written back
   int rvlen = 0;
   int region = 0;            // floats per warp-private accumulator region
+  // passes of up to this many 8-point batches per warp run on pinn_fused_small_kernel (four lanes per point): the
+  // reference's own batch sizes (N_f = 1000 ... 10 771); PINN_FUSED_SMALL_ROUNDS overrides, 0 disables
+  int small_rounds = 1;
 };
 
 // decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates

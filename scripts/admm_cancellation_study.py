@@ -71,7 +71,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child(sys.argv[2] == "1")
     else:
-        libs = [None] + sorted(glob.glob(os.path.join(ROOT, "scripts", "variants", "libpinn_*.so")))
+        libs = [None] + sorted(glob.glob(os.path.join(ROOT, "scripts", "variants", "libpinn_t[0-9]*.so")))
         for k, lib in enumerate(libs):
             env = dict(os.environ)
             if lib:

@@ -54,7 +54,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for lib in sorted(glob.glob(os.path.join(ROOT, "scripts", "variants", "libpinn_*.so"))):
+        for lib in sorted(glob.glob(os.path.join(ROOT, "scripts", "variants", "libpinn_t[0-9]*.so"))):
             print(os.path.basename(lib), flush=True)
             env = dict(os.environ, PINN_B200_LIB=lib)
             subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)

@@ -15,7 +15,7 @@ Schedules (shared with the GPU test through converged_schedule):
                   Adam steps then L-BFGS-B with the reference's options (AB-L2:68-72), at most 15 000 iterations.
   identification  config 2: N_u = 2000 interior samples, N_f = 2000 fixed uniform points, loss AB-L2:59-60, lambda TRAINABLE
                   from (0, 0.0031831 -- ID-L2b:90), 2000 Adam steps then L-BFGS-B over (theta, lambda) with the options of
-                  AB-ADMM:68-72 (at most 5000 iterations, ftol 1e-7).
+                  AB-ADMM:68-72 (at most 5000 iterations) and ftol = 1e-9.
   euler_admm      config 3: Abgrall_eulers, [2,200x5,3], N_data = 200, N_f = 1000 re-drawn every epoch (EUL:232-235), pen = 40,
                   the reference's ADMM loss and z/lagrange updates (EUL:128-141,:237-242), train(3000) = 2999 Adam epochs.
   euler_mse       the same with the plain-MSE residual loss.
@@ -55,11 +55,13 @@ def converged_schedule(which):
         return g, layers, theta0, prob, sched
     if which == "identification":
         g, layers, theta0, prob, _ = trajectory_schedule("identification")
-        # L-BFGS-B with the options of Abgrall_ADMM.py:68-72 (ftol 1e-7): the run stops when the loss stalls, long before
+        # L-BFGS-B with the options of Abgrall_ADMM.py:68-72 but ftol 1e-9: the run stops when the loss stalls, before
         # float32 rounding noise defeats the line search -- with Abgrall_L2.py's ftol = eps the float32 runs stop anywhere
         # between 2400 and 3700 iterations (error_u 0.032 ... 0.039, lambda1 0.957 ... 0.969; float64: 10 000 iterations,
         # 0.015, 0.999) and no two float32 evaluation orders end in the same place
-        return g, layers, theta0, prob, dict(adam_steps=2000, lbfgs=dict(LBFGS_AB_ADMM))
+        # (AB-ADMM's own ftol = 1e-7 is relative to max(|loss|, 1): with a loss of 1e-2 it stops L-BFGS-B at its first
+        # iterations; 1e-9 sits between that and the float32 noise of the loss, ~1e-10)
+        return g, layers, theta0, prob, dict(adam_steps=2000, lbfgs=dict(LBFGS_AB_ADMM, ftol=1e-9))
     sol = dict(np.load(os.path.join(HERE, "data", "Abgrall_eulers.npz")))
     g = odata.euler_inputs(sol, N_data=200, N_f=1000, seed=1234)   # seeds numpy's legacy RNG; later batches continue its stream
     layers = [2] + [200] * 5 + [3]

@@ -39,6 +39,8 @@ def _worker(rank, world, port, n_total, out, peer, loss="v4"):
         eng.set_data(X_u, np.sin(X_u[:, 0:1]))
         first, cnt = shard_range(n_total, rank, world)
         eng.sample_collocation(1234, first, cnt, n_total)
+        if loss == "v5":
+            eng.admm_init()   # z = gamma = 1, z <- f(theta0): per-point state, sharded with the points
         st = DataParallelStepper(eng, rank, world, peer_memory=peer)
         # INF-L2's un-squared data norm is excluded from the in-kernel exchange (its data gradient can join the packed
         # vector after the reduction kernel): the stepper falls back to the allreduce on every rank
@@ -62,16 +64,17 @@ def _worker(rank, world, port, n_total, out, peer, loss="v4"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer,loss", [(False, "v4"), (True, "v4"), (True, "v1"), (False, "v1")],
-                         ids=["nccl", "peer-memory", "v1-asks-for-peer-memory", "v1-nccl"])
-def test_two_gpu_sharded_gradient_equals_single_gpu(peer, loss):
+@pytest.mark.parametrize("peer,loss,n_total", [(False, "v4", 200001), (True, "v4", 200001), (True, "v1", 200001), (False, "v1", 200001),
+                                               (True, "v4", 4001), (False, "v5", 4001)],
+                         ids=["nccl", "peer-memory", "v1-asks-for-peer-memory", "v1-nccl", "peer-memory-small-batch-kernel",
+                              "nccl-small-batch-kernel-admm"])
+def test_two_gpu_sharded_gradient_equals_single_gpu(peer, loss, n_total):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from pinns_b200 import Engine
     from pinns_b200.models import xavier_init_flat
-    n_total = 200001
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
@@ -89,6 +92,8 @@ def test_two_gpu_sharded_gradient_equals_single_gpu(peer, loss):
     X_u = np.array([-1, 0]) + np.array([2, 0.99]) * rng.random((50, 2))
     eng.set_data(X_u, np.sin(X_u[:, 0:1]))
     eng.sample_collocation(1234, 0, n_total, n_total)
+    if loss == "v5":
+        eng.admm_init()
     eng.loss_grad_device()
     eng.synchronize()
     packed1 = eng.packed_tensor().cpu().numpy().copy()

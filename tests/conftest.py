@@ -4,6 +4,11 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The oracle's torch graphs are thousands of tiny ops (10^3 .. 10^4 points, width 20): with one thread per core the intra-op
+# pool spends its time spinning (measured here: a reference replay 114 s with 8 threads, 12 s with <= 4).  Must be set
+# before torch starts its pools; spawned ranks of the gloo tests inherit it.
+os.environ.setdefault("OMP_NUM_THREADS", str(min(4, os.cpu_count() or 1)))
+os.environ.setdefault("MKL_NUM_THREADS", os.environ["OMP_NUM_THREADS"])
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

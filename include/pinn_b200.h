@@ -118,6 +118,13 @@ int pinn_feed_collocation(pinn_handle_t h, const float* X_f_host, int64_t n_f, i
  * counter-based Philox4x32-10, point i of the job uses counter (first_index + i), so the
  * stream is independent of how the job is sharded over GPUs.                            */
 int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index, int64_t n_f, int64_t nf_global);
+/* device-side replacement of `lb + (ub - lb) * lhs(2, N_f)` (pyDOE, INF-L2:183, INF-ADMM:270): a Latin hypercube design
+ * of n_design points over [lb, ub) -- one point in each of the n_design strata of either axis -- of which this handle
+ * takes points [first_index, first_index + n_f).  The stratum of point i along axis d is a keyed bijection of i
+ * (Feistel network, cycle-walked), the offset inside it a Philox4x32-10 uniform: point i depends on (seed, i, n_design)
+ * only, so the design is the same however it is sharded over GPUs.  Float64 arithmetic, one rounding to float32 (the
+ * reference's feed-time cast).  Same distribution as pyDOE's default, not NumPy's stream.  n_design = 0: n_f.        */
+int pinn_sample_lhs(pinn_handle_t h, uint64_t seed, uint64_t first_index, int64_t n_f, int64_t n_design, int64_t nf_global);
 int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device);
 /* scale applied to the data term of loss and gradient (1 on the rank that owns it, 0 elsewhere) */
 int pinn_set_data_weight(pinn_handle_t h, float w);

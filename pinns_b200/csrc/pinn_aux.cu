@@ -1,5 +1,5 @@
 // Small kernels around the hot path: weight repacking, deterministic cross-CTA
-// reduction, data-term seeds, TF-1 Adam, Philox collocation sampler.
+// reduction, data-term seeds, TF-1 Adam, Philox collocation sampler, Latin hypercube design.
 #include "pinn_kernels.h"
 
 namespace {
@@ -99,6 +99,57 @@ __global__ void sample_kernel(float* __restrict__ X, int64_t n, uint64_t seed, u
   }
 }
 
+// Latin hypercube sample, one thread per point, no sort and no second pass: the stratum of point i along dimension d is
+// pi_d(i), a keyed bijection of [0, N) (balanced Feistel network over the next even power of two, cycle-walked back into
+// the range), so every stratum of every dimension is hit exactly once and point i is a pure function of (seed, i, N) --
+// any rank can produce any slice of the design.  Arithmetic in float64 with explicit roundings (the reference forms
+// lb + (ub - lb) * lhs(2, N_f) in float64, INF-L2:183, and casts at feed time): oracle/philox.py restates it bit for bit.
+__device__ __forceinline__ uint32_t lhs_round(uint32_t r, uint32_t round, uint32_t dim, uint32_t k0, uint32_t k1) {
+  uint32_t h = r ^ (k0 + round * 0x9E3779B9u);
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h += k1 ^ ((dim + 1u) * 0xC2B2AE35u);
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__device__ __forceinline__ uint64_t lhs_perm(uint64_t i, uint64_t N, int half_bits, uint32_t dim, uint32_t k0, uint32_t k1) {
+  const uint32_t mask = (half_bits >= 32) ? 0xFFFFFFFFu : ((1u << half_bits) - 1u);
+  do {
+    uint32_t L = (uint32_t)(i >> half_bits) & mask, R = (uint32_t)i & mask;
+#pragma unroll
+    for (uint32_t r = 0; r < 6; ++r) {
+      const uint32_t F = lhs_round(R, r, dim, k0, k1) & mask;
+      const uint32_t t = L ^ F;
+      L = R;
+      R = t;
+    }
+    i = ((uint64_t)L << half_bits) | (uint64_t)R;
+  } while (i >= N);
+  return i;
+}
+
+__global__ void lhs_kernel(float* __restrict__ X, int64_t n, uint64_t seed, uint64_t first, uint64_t N, int half_bits,
+                           double lbx, double lbt, double wx, double wt) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = first + (uint64_t)i;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), 1u, 0u, k0, k1, o);  // counter word 2 = 1: not the uniform sampler's stream
+    const double u0 = (double)(o[0] >> 8) * 5.9604644775390625e-08;    // 2^-24, exact
+    const double u1 = (double)(o[1] >> 8) * 5.9604644775390625e-08;
+    const double s0 = (double)lhs_perm(c, N, half_bits, 0u, k0, k1);
+    const double s1 = (double)lhs_perm(c, N, half_bits, 1u, k0, k1);
+    const double h0 = __ddiv_rn(__dadd_rn(s0, u0), (double)N);          // in [s/N, (s+1)/N)
+    const double h1 = __ddiv_rn(__dadd_rn(s1, u1), (double)N);
+    float2 xt;
+    xt.x = __double2float_rn(__dadd_rn(lbx, __dmul_rn(wx, h0)));
+    xt.y = __double2float_rn(__dadd_rn(lbt, __dmul_rn(wt, h1)));
+    *reinterpret_cast<float2*>(X + 2 * i) = xt;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -181,6 +232,16 @@ cudaError_t pinn_sample_launch(float* X, int64_t n, uint64_t seed, uint64_t firs
                                float spant, cudaStream_t stream) {
   const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
   sample_kernel<<<grid > 0 ? grid : 1, 256, 0, stream>>>(X, n, seed, first_index, lbx, lbt, spanx, spant);
+  return cudaGetLastError();
+}
+
+cudaError_t pinn_lhs_launch(float* X, int64_t n, uint64_t seed, uint64_t first_index, uint64_t n_total, double lbx, double lbt,
+                            double wx, double wt, cudaStream_t stream) {
+  int bits = 2;
+  while (bits < 64 && (bits == 64 ? 0 : (1ull << bits)) < n_total) ++bits;
+  if (bits & 1) ++bits;  // balanced halves
+  const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  lhs_kernel<<<grid > 0 ? grid : 1, 256, 0, stream>>>(X, n, seed, first_index, n_total, bits / 2, lbx, lbt, wx, wt);
   return cudaGetLastError();
 }
 

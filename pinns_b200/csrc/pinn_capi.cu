@@ -722,6 +722,27 @@ int pinn_sample_collocation(pinn_handle_t h, uint64_t seed, uint64_t first_index
   return PINN_OK;
 }
 
+int pinn_sample_lhs(pinn_handle_t h, uint64_t seed, uint64_t first_index, int64_t n_f, int64_t n_design, int64_t nf_global) {
+  if (!h || n_f <= 0) return PINN_E_INVALID;
+  if (n_design <= 0) n_design = n_f;
+  REQUIRE(first_index + (uint64_t)n_f <= (uint64_t)n_design, PINN_E_INVALID,
+          "pinn_sample_lhs: [first_index, first_index + n_f) must lie inside the design of n_design points");
+  REQUIRE((uint64_t)n_design <= (1ull << 48), PINN_E_INVALID, "pinn_sample_lhs: designs beyond 2^48 points are not supported");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = feed_join(h);
+  if (rc) return rc;
+  rc = ensure_xf_owned(h, n_f);
+  if (rc) return rc;
+  CK(pinn_lhs_launch(h->d_Xf_owned, n_f, seed, first_index, (uint64_t)n_design, h->cfg.lb[0], h->cfg.lb[1],
+                     h->cfg.ub[0] - h->cfg.lb[0], h->cfg.ub[1] - h->cfg.lb[1], h->stream));
+  h->launches += 1;
+  h->d_Xf = h->d_Xf_owned;
+  h->n_f = n_f;
+  h->nf_global = nf_global > 0 ? nf_global : n_f;
+  h->l1_ready = false;
+  return PINN_OK;
+}
+
 int pinn_get_collocation(pinn_handle_t h, float* X_f, int on_device) {
   if (!h || !X_f) return PINN_E_INVALID;
   REQUIRE(h->d_Xf && h->n_f > 0, PINN_E_STATE, "pinn_get_collocation: no collocation points set");

@@ -65,5 +65,7 @@ cudaError_t pinn_adam_launch(float* theta, const float* packed, AdamState st, in
                              float eps, cudaStream_t stream);
 cudaError_t pinn_sample_launch(float* X, int64_t n, uint64_t seed, uint64_t first_index, float lbx, float lbt, float spanx,
                                float spant, cudaStream_t stream);
+cudaError_t pinn_lhs_launch(float* X, int64_t n, uint64_t seed, uint64_t first_index, uint64_t n_total, double lbx, double lbt,
+                            double wx, double wt, cudaStream_t stream);
 cudaError_t pinn_fill_launch(float* p, int64_t n, float v, cudaStream_t stream);
 cudaError_t pinn_fma_peak(double* tflops);

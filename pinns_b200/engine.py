@@ -219,6 +219,13 @@ class Engine:
                  "pinn_sample_collocation")
         self.n_f = int(n_f)
 
+    def sample_lhs(self, seed: int, n_f: int, first_index: int = 0, n_design: int = 0, nf_global: int = 0):
+        """`lb + (ub - lb) * lhs(2, N_f)` on the device (INF-L2:183): points [first_index, first_index + n_f) of a Latin
+        hypercube design of n_design points (default n_f)."""
+        self._ck(capi.lib.pinn_sample_lhs(self._h, int(seed), int(first_index), int(n_f), int(n_design), int(nf_global)),
+                 "pinn_sample_lhs")
+        self.n_f = int(n_f)
+
     def get_collocation(self) -> np.ndarray:
         out = np.empty((self.n_f, 2), np.float32)
         self._ck(capi.lib.pinn_get_collocation(self._h, out.ctypes.data_as(C.c_void_p), 0), "pinn_get_collocation")

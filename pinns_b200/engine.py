@@ -231,6 +231,13 @@ class Engine:
         self._ck(capi.lib.pinn_get_collocation(self._h, out.ctypes.data_as(C.c_void_p), 0), "pinn_get_collocation")
         return out
 
+    def get_collocation_device(self, out):
+        """Copies the current collocation batch into `out`, a float32 [n_f, 2] torch tensor on this engine's GPU."""
+        assert out.is_cuda and out.is_contiguous() and out.numel() == 2 * self.n_f
+        self._ck(capi.lib.pinn_get_collocation(self._h, C.c_void_p(out.data_ptr()), 1), "pinn_get_collocation")
+        self.synchronize()
+        return out
+
     # ---- hot path ----
     def loss_grad(self, want_grad: bool = True) -> Tuple[float, Optional[np.ndarray]]:
         """One sess.run([loss, grads]): residual + loss + full parameter gradient."""

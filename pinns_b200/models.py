@@ -94,6 +94,19 @@ class _Base:
     def neural_net(self, X, weights=None, biases=None):
         return self.engine.predict(np.asarray(X), want_f=False)[0]
 
+    def lhs_collocation_on_device(self, N_f: int, seed: int = 1234, rank: int = 0, world: int = 1) -> np.ndarray:
+        """`X_f_train = lb + (ub - lb) * lhs(2, N_f)` (INF-L2:183, INF-ADMM:270) drawn ON THE DEVICE: a Latin hypercube
+        design of N_f points (pinn_sample_lhs: Philox offsets, Feistel stratum permutations); with world > 1 this rank
+        takes its contiguous slice of the same design.  Becomes the engine's collocation batch; the host copy is returned
+        for the class attributes x_f / t_f.  (The reference appends its IC/BC points to the design, INF-L2:184: callers
+        that want them keep passing X_f through the constructor.)"""
+        from .distributed import shard_range
+        first, cnt = shard_range(int(N_f), rank, world)
+        self.engine.sample_lhs(seed, cnt, first_index=first, n_design=int(N_f), nf_global=int(N_f))
+        X = self.engine.get_collocation()
+        self.x_f, self.t_f = X[:, 0:1], X[:, 1:2]
+        return X
+
     def train_step_from_host(self, X_f_host, nf_global: int = 0, stepper=None) -> float:
         """One `sess.run(train_op_Adam, feed_dict)` with the collocation points fed from HOST memory
         (INF-L2:127-135 re-feeds them every step): H2D copy of X_f (float32 [N,2] torch tensor, ideally

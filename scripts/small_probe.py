@@ -4,7 +4,7 @@ sys.path.insert(0, '/root/repo')
 from pinns_b200 import Engine
 from tests.helpers import rand_theta
 B20 = [2] + [20] * 8 + [1]
-for n_f, loss, n_u in ((1000, 'v5', 100), (5000, 'v5', 100), (10456, 'v1', 100), (2000, 'v4', 2000), (20000, 'v4', 100), (37000, 'v4', 100)):
+for n_f, loss, n_u in ((1000, 'v5', 100), (5000, 'v5', 100), (9372, 'v1', 100), (10456, 'v1', 100), (10771, 'v1', 100), (2000, 'v4', 2000), (20000, 'v4', 100), (37000, 'v4', 100)):
     eng = Engine(B20, [-1, 0], [1, 0.99], loss=loss, lambda2=0.01 / np.pi, rho=10.0)
     eng.use_torch_stream()
     eng.set_params(rand_theta(B20, np.random.default_rng(0)))

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import tf_graph as tg
 from oracle.optim import TF1Adam
-from oracle.philox import sample_collocation
+from oracle.philox import sample_collocation, sample_lhs
 from tests.helpers import make_case, make_engine, rel_err, max_rel_err
 
 pytestmark = pytest.mark.gpu
@@ -100,6 +100,42 @@ def test_device_sampler_is_bit_exact_and_shard_invariant():
     big = (1 << 40) + 7
     eng.sample_collocation(99, big, 33)
     assert np.array_equal(eng.get_collocation(), sample_collocation(99, big, 33, c["prob"].lb, c["prob"].ub))
+
+
+def test_device_lhs_is_bit_exact_shard_invariant_and_latin():
+    """pinn_sample_lhs (INF-L2:183 `lb + (ub - lb) * lhs(2, N_f)` on the device) against its numpy restatement, bit for bit
+    (integer permutation + Philox + float64 arithmetic with explicit roundings); slices of a design; and the Latin
+    property at the size of BASELINE config 4's largest batch, counted on the device."""
+    import torch
+    c = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V4, 10, 64, seed=1)
+    eng = make_engine(c)
+    lb, ub = c["prob"].lb, c["prob"].ub
+    for n in (1, 2, 7, 1000, 10000, 65537):
+        eng.sample_lhs(1234, n)
+        assert np.array_equal(eng.get_collocation(), sample_lhs(1234, 0, n, n, lb, ub)), n
+    eng.sample_lhs(1234, 10000)
+    full = eng.get_collocation()
+    eng.sample_lhs(1234, 2500, first_index=7000, n_design=10000)           # a rank's slice of the same design
+    assert np.array_equal(eng.get_collocation(), full[7000:9500])
+    eng.sample_lhs(77, 3000, first_index=(1 << 33) + 5, n_design=(1 << 33) + 4000)  # 64-bit indices, 34-bit Feistel domain
+    assert np.array_equal(eng.get_collocation(), sample_lhs(77, (1 << 33) + 5, 3000, (1 << 33) + 4000, lb, ub))
+    with pytest.raises(RuntimeError):
+        eng.sample_lhs(1, 100, first_index=950, n_design=1000)             # slice beyond the design
+    lo = torch.tensor(np.asarray(lb, np.float64), device="cuda")
+    w = torch.tensor(np.asarray(ub, np.float64) - np.asarray(lb, np.float64), device="cuda")
+    for n in (1 << 18, 1 << 24):
+        eng.sample_lhs(5, n)
+        X = torch.empty((n, 2), dtype=torch.float32, device="cuda")
+        eng.get_collocation_device(X)
+        Xd = X.double()
+        for d in (0, 1):
+            # sorted along an axis, point i sits in stratum i: within one stratum width of its centre (+ the float32 cast)
+            centre = lo[d] + w[d] * (torch.arange(n, device="cuda").double() + 0.5) / n
+            assert float((Xd[:, d].sort().values - centre).abs().max()) <= 0.5 * float(w[d]) / n + 1.3e-7
+            if n == 1 << 18:   # strata 64 float32 ulps wide: the cast moves few points across an edge
+                cnt = torch.bincount(torch.clamp(torch.floor((Xd[:, d] - lo[d]) / w[d] * n).long(), 0, n - 1), minlength=n)
+                assert int(cnt.max()) <= 2 and int((cnt == 0).sum()) <= n // 20, (d, int(cnt.max()), int((cnt == 0).sum()))
+        del X, Xd
 
 
 @pytest.mark.parametrize("path", ["generic", "auto"])

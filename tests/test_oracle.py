@@ -11,7 +11,7 @@ from oracle import data as odata
 from oracle import taylor as ty
 from oracle import tf_graph as tg
 from oracle.optim import TF1Adam, lbfgs_minimize
-from oracle.philox import philox4x32_10, sample_collocation
+from oracle.philox import lhs_perm, philox4x32_10, sample_collocation, sample_lhs
 from tests.helpers import make_case
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -201,6 +201,37 @@ def test_philox_known_answer_and_sharding_invariance():
     assert np.array_equal(full, parts)
     assert full[:, 0].min() >= -1 and full[:, 0].max() < 1 and full[:, 1].min() >= 0 and full[:, 1].max() < 0.99
     assert abs(full[:, 0].mean()) < 0.1
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 100, 1000, 10000])
+def test_device_lhs_restatement_is_a_latin_hypercube(n):
+    """pinn_sample_lhs's restatement (oracle.philox.sample_lhs) has the defining property of pyDOE.lhs (INF-L2:183,
+    oracle.data.lhs): exactly one point in each of the n strata of either axis; any slice of the design can be produced
+    on its own; the two axes use independent permutations."""
+    lb, ub = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+    for d in (0, 1):
+        assert sorted(lhs_perm(np.arange(n), n, d, 1234).tolist()) == list(range(n))     # a bijection of [0, n)
+    X = sample_lhs(1234, 0, n, n, lb, ub)
+    assert X.dtype == np.float32 and X.shape == (n, 2)
+    strata = np.floor((X.astype(np.float64) - lb) / (ub - lb) * n + 1e-6 * (n <= 1000)).astype(np.int64)
+    strata = np.minimum(strata, n - 1)            # float32 rounding of the last stratum's upper end
+    if n <= 1000:                                 # (beyond that the float32 cast may move a point across a stratum edge)
+        for d in (0, 1):
+            assert np.array_equal(np.sort(strata[:, d]), np.arange(n))
+    else:
+        for d in (0, 1):
+            assert np.abs(np.sort(strata[:, d]) - np.arange(n)).max() <= 1
+    if n >= 100:
+        a, b = n // 3, n - n // 3
+        assert np.array_equal(np.vstack([sample_lhs(1234, 0, a, n, lb, ub), sample_lhs(1234, a, b, n, lb, ub)]), X)
+        p0, p1 = lhs_perm(np.arange(n), n, 0, 1234).astype(float), lhs_perm(np.arange(n), n, 1, 1234).astype(float)
+        assert abs(np.corrcoef(p0, p1)[0, 1]) < 4.0 / np.sqrt(n)                         # axes permuted independently
+        assert abs(np.corrcoef(np.arange(n), p0)[0, 1]) < 4.0 / np.sqrt(n)               # ... and not in index order
+        assert not np.array_equal(sample_lhs(1235, 0, n, n, lb, ub), X)
+        # same marginals as the reference's host construction: both are stratified uniforms
+        from oracle.data import lhs
+        H = lb + (ub - lb) * lhs(2, n, rng=np.random.RandomState(0))
+        assert np.abs(np.sort(H[:, 0]) - np.sort(X[:, 0].astype(np.float64))).max() <= 2.0 / n + 1e-6
 
 
 def test_autograd_vs_taylor_on_random_ragged_nets():

@@ -17,6 +17,9 @@ struct TensorState {
   void* d_units = nullptr;   // the tile schedule (contraction units / worker items), built once per shape
   void* d_items = nullptr;
   int nu_f = 0, nu = 0, ni_f = 0, ni = 0;
+  // TMA tensor maps over the scratch slab (three CUtensorMap objects: rows of 128 B, boxes of 32 / 32 / 128 rows, written
+  // to shared memory with the 32-byte-atom swizzle the MN-major operands need or the 128-byte swizzle of the K-major ones)
+  alignas(64) unsigned char tmaps[3][128] = {};
 };
 
 // AUTO uses the tensor kernel from this many points on: below it the job has fewer 128-point tiles than the GPU has SMs

@@ -134,7 +134,7 @@ def test_device_lhs_is_bit_exact_shard_invariant_and_latin():
             assert float((Xd[:, d].sort().values - centre).abs().max()) <= 0.5 * float(w[d]) / n + 1.3e-7
             if n == 1 << 18:   # strata 64 float32 ulps wide: the cast moves few points across an edge
                 cnt = torch.bincount(torch.clamp(torch.floor((Xd[:, d] - lo[d]) / w[d] * n).long(), 0, n - 1), minlength=n)
-                assert int(cnt.max()) <= 2 and int((cnt == 0).sum()) <= n // 20, (d, int(cnt.max()), int((cnt == 0).sum()))
+                assert int(cnt.max()) <= 3 and int((cnt == 0).sum()) <= n // 20, (d, int(cnt.max()), int((cnt == 0).sum()))
         del X, Xd
 
 

@@ -26,12 +26,12 @@ __global__ void repack_kernel(const NetDesc net, const float* __restrict__ theta
 }
 
 // packed[k] (+)= sum over CTA rows, fixed order, double accumulation -> run-to-run reproducible
-__global__ void finalize_kernel(const float* __restrict__ part, int nrows, int rvlen, float* __restrict__ packed,
+__global__ void finalize_kernel(const float* __restrict__ part, int nrows, int rvlen, int stride, float* __restrict__ packed,
                                 int accumulate, const float* __restrict__ extra, int extra_idx) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= rvlen) return;
   double s = 0.0;
-  for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * rvlen + k];
+  for (int r = 0; r < nrows; ++r) s += (double)part[(size_t)r * stride + k];
   if (extra != nullptr && k == extra_idx) s += (double)extra[0];
   packed[k] = accumulate ? (float)((double)packed[k] + s) : (float)s;
 }
@@ -211,8 +211,9 @@ cudaError_t pinn_repack_launch(const NetDesc& net, const float* theta, float* wp
 }
 
 cudaError_t pinn_finalize_launch(const float* part, int nrows, int rvlen, float* packed, int accumulate, const float* extra,
-                                 int extra_idx, cudaStream_t stream) {
-  finalize_kernel<<<(rvlen + 127) / 128, 128, 0, stream>>>(part, nrows, rvlen, packed, accumulate, extra, extra_idx);
+                                 int extra_idx, cudaStream_t stream, int stride) {
+  finalize_kernel<<<(rvlen + 127) / 128, 128, 0, stream>>>(part, nrows, rvlen, stride > 0 ? stride : rvlen, packed, accumulate, extra,
+                                                          extra_idx);
   return cudaGetLastError();
 }
 

@@ -923,7 +923,7 @@ static int residual_pass(pinn_handle_t h, int mode, int admm_op, bool fuse_adam 
                     state ? h->d_z : nullptr, state ? h->d_gamma : nullptr, admm_op, nullptr, nullptr, &grid, h->stream, h->err);
     if (rc) return rc;
     if (e1) CK(cudaEventRecord(e1, h->stream));
-    CK(pinn_finalize_launch(h->tensor.d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream));
+    CK(pinn_finalize_launch(h->tensor.d_part, grid, h->rvlen, h->d_packed, 0, nullptr, -1, h->stream, h->tensor.part_stride));
     h->launches += 2;
     return PINN_OK;
   }

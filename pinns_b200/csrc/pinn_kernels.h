@@ -54,7 +54,7 @@ cudaError_t pinn_generic_dual_launch(const GenParams& g, int S, int grid_res, co
 // small kernels (pinn_aux.cu)
 cudaError_t pinn_repack_launch(const NetDesc& net, const float* theta, float* wp, float* wt, cudaStream_t stream);
 cudaError_t pinn_finalize_launch(const float* part, int nrows, int rvlen, float* packed, int accumulate, const float* extra,
-                                 int extra_idx, cudaStream_t stream);
+                                 int extra_idx, cudaStream_t stream, int stride = 0);
 cudaError_t pinn_data_seed_launch(const float* u_pred, const float* u_data, int64_t n_u, int n_out, int loss, float weight,
                                   float* seed, float* loss_out, cudaStream_t stream);
 struct AdamState {

@@ -12,7 +12,8 @@ struct TensorState {
   size_t scratch_stride = 0;
   float* d_scratch = nullptr;
   float* d_wcan = nullptr;   // canonical hi/lo TF32 weight planes
-  float* d_part = nullptr;   // [grid][rvlen]
+  float* d_part = nullptr;   // [grid][part_stride]: a CTA's partial packed vector, 16-byte aligned (part_stride = rvlen rounded up to 4)
+  int part_stride = 0;
   int* d_hang = nullptr;     // set by the kernel if an mbarrier wait times out
   void* d_units = nullptr;   // the tile schedule (contraction units / worker items), built once per shape
   void* d_items = nullptr;

@@ -46,7 +46,8 @@ struct FusedState {
   // passes of up to this many 8-point batches per warp run on pinn_fused_small_kernel (four lanes per point): the
   // reference's own batch sizes (N_f = 1000 ... 10 771); PINN_FUSED_SMALL_ROUNDS overrides, 0 disables
   int small_rounds = 1;
-  int small_extra = 1;   // of every 8 warps, how many may take one batch more than small_rounds
+  int small_extra = 1;   // warps per CTA that may take one batch more than small_rounds
+  int small_nine = 1;    // nine warps per CTA when eight do not give every batch a warp of its own
 };
 
 // decides whether the net qualifies (Burgers, [2, H x k, 1] with a supported H) and allocates

@@ -8,7 +8,7 @@ struct TensorState {
   bool forced = false;       // PINN_PATH_TENSOR: use it whatever the batch size
   int n = 0, NL = 0, grid_max = 0, rvlen = 0;
   int S = 4, NO = 1;         // Taylor streams (4 Burgers, 3 Euler), outputs (1 / 3)
-  int shape[10] = {};        // the kernel's TcShape (padded width, column blocks, chunk sizes)
+  int shape[11] = {};        // the kernel's TcShape (padded width, column blocks, chunk sizes)
   size_t scratch_stride = 0;
   float* d_scratch = nullptr;
   float* d_wcan = nullptr;   // canonical hi/lo TF32 weight planes

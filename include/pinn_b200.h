@@ -59,10 +59,10 @@ typedef struct pinn_handle_s* pinn_handle_t;
 #define PINN_LOSS_V5_ADMM 5       /* (1/Nu)||r||^2 + (rho/2)||f - z + g/rho||^2 (per residual) AB-ADMM:129-130, EUL:128-133 */
 
 /* kernel selection */
-#define PINN_PATH_AUTO 0    /* fused thread-per-point kernel for [2,20xk,1]; tcgen05 kernel for wide Burgers nets at N_f >= 8192; else generic */
+#define PINN_PATH_AUTO 0    /* fused thread-per-point kernels for [2,20xk,1]; tcgen05 kernel for wide Burgers / Euler nets at N_f >= 8192; else generic */
 #define PINN_PATH_GENERIC 1 /* force the generic tiled FP32 kernel */
 #define PINN_PATH_FUSED 2   /* force the fused kernel (error if the net does not qualify) */
-#define PINN_PATH_TENSOR 3  /* tcgen05/TMEM 3xTF32 kernel for wide Burgers nets [2, n x k, 1], n in {32,64,96,128} */
+#define PINN_PATH_TENSOR 3  /* tcgen05 / TMEM / TMA 3xTF32 kernel: Burgers [2, n x k, 1] and Euler [2, n x k, 3], equal hidden widths 32 <= n <= 256 */
 
 #define PINN_MAX_LAYERS 16
 

@@ -47,6 +47,7 @@ struct FusedState {
   // reference's own batch sizes (N_f = 1000 ... 10 771); PINN_FUSED_SMALL_ROUNDS overrides, 0 disables
   int small_rounds = 1;
   int small_extra = 1;   // warps per CTA that may take one batch more than small_rounds
+  int small_compact = 1; // the small-batch kernel merges the two k-group copies of a tile slot before the store (half the lines to reduce)
   int small_nine = 1;    // nine warps per CTA when eight do not give every batch a warp of its own
 };
 

@@ -318,6 +318,25 @@ def test_v1_norm_inside_the_fused_pass_and_its_fallback():
     assert np.isfinite(l0) and np.isnan(g0).any()
 
 
+@pytest.mark.parametrize("nine", ["1", "0"], ids=["nine-warps", "second-batch-on-one-warp-per-SM"])
+@pytest.mark.parametrize("loss", [tg.LOSS_V4, tg.LOSS_V5], ids=["v4", "v5-admm"])
+def test_config1_sized_batch_stays_on_the_small_batch_kernel(nine, loss, monkeypatch):
+    """INF-L2 / INF-ADMM's 10 456 + 100 points are 1320 batches of 8 points for 1184 warps: the small-batch kernel runs them with
+    nine warps per CTA (default) or, PINN_FUSED_SMALL_NINE=0, with a second batch on one warp per SM.  Both against the oracle,
+    bit-reproducible, and the ADMM state they leave is the same."""
+    monkeypatch.setenv("PINN_FUSED_SMALL_NINE", nine)
+    c = make_case(tg.PDE_BURGERS, B20, loss, 100, 10456, seed=41)
+    ref = tg.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], c["X_f"], z=c.get("z"), gamma=c.get("gamma"))
+    eng = make_engine(c)
+    assert eng.kernel_path == "fused"
+    n0 = eng.launch_count
+    l1, g1 = eng.loss_grad()
+    assert eng.launch_count - n0 == 2
+    l2, g2 = eng.loss_grad()
+    assert l1 == l2 and np.array_equal(g1, g2)
+    assert abs(l1 - ref.loss) <= TOL * abs(ref.loss) and rel_err(g1, ref.grad) <= TOL
+
+
 def test_tensor_path_run_to_run_determinism():
     """tcgen05 path: per-CTA partial gradients are updated with red.global.add by a fixed thread per element and summed
     over CTAs in fixed order -> bit-identical loss and gradient from run to run"""

@@ -48,6 +48,7 @@ struct FusedState {
   int small_rounds = 1;
   int small_extra = 1;   // warps per CTA that may take one batch more than small_rounds
   int small_compact = 1; // the small-batch kernel merges the two k-group copies of a tile slot before the store (half the lines to reduce)
+  int pdl = 1;           // programmatic dependent launch of the small-batch kernel and its reduction
   int small_nine = 1;    // nine warps per CTA when eight do not give every batch a warp of its own
 };
 

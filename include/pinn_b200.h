@@ -184,6 +184,17 @@ int pinn_admm_update(pinn_handle_t h, int inf_admm_quirk); /* z_update then gamm
  * Equivalent, bit for bit, to pinn_admm_update(h, inf_admm_quirk) followed by pinn_adam_steps(h, 1)
  * (INF-ADMM:189-193 with inf_admm_quirk = 1).                                                            */
 int pinn_admm_adam_step(pinn_handle_t h, int inf_admm_quirk);
+/* n_epochs iterations of the batch loops of the Dialect-B scripts with the device sampler, without returning to the host
+ * (AB-ADMM:211-226, EUL:227-242, AB-L2:205-210: Adam step on the current batch, new batch, z/gamma update on it):
+ *   epoch k:  pending ? pinn_admm_adam_step(h, 0) : pinn_adam_steps(h, 1);
+ *             pinn_sample_collocation(h, seed, (first_batch + k) * n_f, n_f, nf_global);
+ *             pending = admm
+ * `pending` says whether a z/gamma update is still owed on entry (it is folded into the first Adam step's pass) and, with
+ * admm = 1, one is owed again on return (the caller folds it into its next step or flushes it with pinn_admm_update).
+ * Same launches, same bits as the calls above made one by one: at the reference's batch sizes an epoch is ~25 us of GPU work
+ * and the per-call host overhead of an interpreted loop was as much again.                                        */
+int pinn_resampled_epochs(pinn_handle_t h, int64_t n_epochs, int admm, int pending, uint64_t seed, uint64_t first_batch,
+                          int64_t n_f, int64_t nf_global);
 int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device); /* [N_f, n_res] each */
 int pinn_admm_set_state(pinn_handle_t h, const float* z, const float* gamma, int on_device);
 

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "pinn_comm_status": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pinn_sample_collocation": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "pinn_sample_lhs": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64]),
+    "pinn_resampled_epochs": (C.c_int, [_H, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64]),
     "pinn_get_collocation": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "pinn_set_data_weight": (C.c_int, [_H, C.c_float]),
     "pinn_loss_grad_device": (C.c_int, [_H]),

@@ -1119,6 +1119,21 @@ int pinn_admm_adam_step(pinn_handle_t h, int quirk) {
   return pinn_adam_apply(h);
 }
 
+int pinn_resampled_epochs(pinn_handle_t h, int64_t n_epochs, int admm, int pending, uint64_t seed, uint64_t first_batch,
+                          int64_t n_f, int64_t nf_global) {
+  if (!h || n_epochs < 0 || n_f <= 0) return PINN_E_INVALID;
+  REQUIRE(!admm || h->cfg.loss == PINN_LOSS_V5_ADMM || h->cfg.loss == PINN_LOSS_V2_INF_ADMM, PINN_E_STATE,
+          "pinn_resampled_epochs: admm = 1 but the loss is not an ADMM loss");
+  for (int64_t k = 0; k < n_epochs; ++k) {
+    int rc = pending ? pinn_admm_adam_step(h, 0) : pinn_adam_steps(h, 1);
+    if (rc) return rc;
+    rc = pinn_sample_collocation(h, seed, (first_batch + (uint64_t)k) * (uint64_t)n_f, n_f, nf_global);
+    if (rc) return rc;
+    pending = admm;
+  }
+  return PINN_OK;
+}
+
 int pinn_predict(pinn_handle_t h, const float* X, int64_t n, float* u_out, float* f_out, int on_device) {
   if (!h || !X || n <= 0) return PINN_E_INVALID;
   CK(cudaSetDevice(h->cfg.device));

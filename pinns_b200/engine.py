@@ -339,6 +339,13 @@ class Engine:
         the same residuals; AB-ADMM:225-226 then :213).  Same bits as admm_update() followed by adam_steps(1)."""
         self._ck(capi.lib.pinn_admm_adam_step(self._h, int(inf_admm_quirk)), "pinn_admm_adam_step")
 
+    def resampled_epochs(self, n_epochs: int, admm: bool, pending: bool, seed: int, first_batch: int, n_f: int, nf_global: int = 0):
+        """n_epochs x (Adam step on the current batch [with the owed z/gamma update folded in], new device-sampled batch):
+        the Dialect-B batch loops (AB-ADMM:211-226, EUL:227-242) without a host round trip per epoch."""
+        self._ck(capi.lib.pinn_resampled_epochs(self._h, int(n_epochs), int(admm), int(pending), int(seed), int(first_batch),
+                                               int(n_f), int(nf_global)), "pinn_resampled_epochs")
+        self.n_f = int(n_f)
+
     def admm_state(self):
         z = np.empty((self.n_f, self.n_res), np.float32)
         g = np.empty((self.n_f, self.n_res), np.float32)

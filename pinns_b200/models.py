@@ -402,6 +402,25 @@ class BurgersIdentification(_Base):
             self.engine.set_collocation(np.hstack([self.x_phys, self.t_phys]))
         self._step_counter += 1
 
+    def _plain_epochs(self, epoch, nEpochs):
+        """How many epochs from `epoch` on end with nothing but the next batch (see train)."""
+        if getattr(self, "_per_epoch_calls", False):
+            return 0
+        if self._resample_each_step and self._resample_mode != "device":
+            return 0
+        if self._admm and not (self._fold_admm and self._resample_each_step):
+            return 0
+        k = 0
+        while epoch + k < nEpochs:
+            e = epoch + k
+            if self._lbfgs_after is not None and e > self._lbfgs_after:
+                break
+            every = 1000 if (self._lbfgs_after is None or e < self._lbfgs_after) else 100
+            if e % 1000 == 0 or (self._record and e % every == 0):
+                break
+            k += 1
+        return k
+
     def callback(self, loss, lambda_1=None, lambda_2=None):                 # AB-ADMM:182-183
         l1, l2 = self.engine.get_lambda()
         print('Loss: %e, l1: %.5f, l2: %.5f' % (loss, l1 if lambda_1 is None else lambda_1, l2 if lambda_2 is None else lambda_2))
@@ -419,6 +438,19 @@ class BurgersIdentification(_Base):
         # (engine.admm_adam_step, same bits), and flushed before anything else looks at the state.
         pending = False
         while epoch < nEpochs:
+            # epochs at whose end nothing but the next batch happens (no print, no record, no L-BFGS) run as ONE call when the
+            # batches come from the device sampler: same launches, same bits, no interpreter between them (the per-epoch host
+            # overhead was as long as the ~25 us of GPU work)
+            k = self._plain_epochs(epoch, nEpochs)
+            if k > 0:
+                if self._resample_each_step:
+                    self.engine.resampled_epochs(k, self._admm, pending, 1234, self._step_counter, self.N_f)
+                    self._step_counter += k
+                    pending = self._admm
+                else:
+                    self.engine.adam_steps(k)
+                epoch += k
+                continue
             if self._lbfgs_after is None or epoch <= self._lbfgs_after:
                 if pending:
                     self.engine.admm_adam_step()
@@ -565,6 +597,17 @@ class EulerInference(_Base):
         epoch = 1
         pending = False   # a z/lagrange update waiting to be folded into the next Adam step's pass (same residuals, same bits)
         while epoch < nEpochs:
+            # plain epochs (no print, no record at their end) with the device sampler: one call, same launches, same bits
+            k = 0
+            if self._resample_mode == "device" and (not self._admm or self._fold_admm) and not getattr(self, "_per_epoch_calls", False):
+                while epoch + k < nEpochs and (epoch + k) % 1000 != 0 and not (self._record and (epoch + k) % 10000 == 0):
+                    k += 1
+            if k > 0:
+                self.engine.resampled_epochs(k, self._admm, pending, 1234, self._step_counter, self.N_f)
+                self._step_counter += k
+                pending = self._admm
+                epoch += k
+                continue
             if pending:
                 self.engine.admm_adam_step()
                 pending = False

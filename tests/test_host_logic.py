@@ -32,6 +32,15 @@ class FakeEngine:
     def admm_update(self, inf_admm_quirk=False): self.calls.append(("admm_update", inf_admm_quirk))
     def admm_adam_step(self, inf_admm_quirk=False):  # one pass on the device; in the reference's order: update, then the Adam step
         self.calls.append(("admm_update", inf_admm_quirk)); self.calls.append(("adam", 1)); self.calls.append(("folded",))
+    def resampled_epochs(self, n_epochs, admm, pending, seed, first_batch, n_f, nf_global=0):
+        # pinn_resampled_epochs: the same calls the per-epoch loop makes, issued inside the library
+        for k in range(n_epochs):
+            if pending:
+                self.admm_adam_step()
+            else:
+                self.adam_steps(1)
+            self.sample_collocation(seed, (first_batch + k) * n_f, n_f, nf_global)
+            pending = bool(admm)
     def predict(self, X, want_f=True):
         n = np.asarray(X).shape[0]
         no = self.layers[-1] if self.layers else 1
@@ -120,6 +129,22 @@ def test_euler_class_schema_and_device_resampling(fake, tmp_path):
     assert len(m.predict(m.X_star[:5])) == 6                 # EUL:260-272 returns six arrays
     m.save_data()
     assert open(str(tmp_path / "e.csv")).readline().strip() == "x,t,rho_pred,u_pred,E_pred,epoch"
+
+
+def test_device_resampled_stretches_issue_the_per_epoch_calls(fake):
+    """With the device sampler the plain epochs of a Dialect-B loop go to the library as one stretch (pinn_resampled_epochs):
+    the operations and their order are those of the epoch-by-epoch loop, prints and flushes at the multiples of 1000 included."""
+    class P(models.Parameters):
+        N_u = 50; N_f = 64; rho = 10.0; epochs = 1; gpu = '0'
+    seqs = []
+    for per_epoch in (True, False):
+        m = models.BurgersIdentification(P(), variant="AB-ADMM", data=os.path.join(GOLD, "TwoSin_burgers_shock.npz"),
+                                         verbose=False, run=False, resample="device")
+        m._per_epoch_calls = per_epoch
+        m.engine.calls.clear()
+        m.train(2005)
+        seqs.append([c for c in m.engine.calls if c[0] in ("adam", "sample", "admm_update", "folded", "loss")])
+    assert seqs[0] == seqs[1] and sum(c[0] == "loss" for c in seqs[0]) == 2 and sum(c[0] == "sample" for c in seqs[0]) == 2004
 
 
 def test_xavier_init_flat_layout():

@@ -63,6 +63,39 @@ def test_identification_and_euler_classes_run():
     assert np.isfinite(e2.error_E)
 
 
+def test_device_resampled_stretches_equal_the_per_epoch_loop_bit_for_bit():
+    """pinn_resampled_epochs (the Dialect-B batch loop inside the library: Adam step [+ folded z/gamma update], new device batch)
+    against the same loop driven epoch by epoch from Python: identical parameters, ADMM state and batch -- across the epoch-1000
+    boundary where the loss print flushes the pending update."""
+    from pinns_b200.models import BurgersIdentification, EulerInference, EulerParameters, Parameters
+
+    class P(Parameters):
+        N_u = 100; N_f = 1000; rho = 10.0; epochs = 1; gpu = '0'
+
+    class E(EulerParameters):
+        N_data = 200; N_f = 1000; pen = 40.0; epochs = 1; gpu = '0'
+
+    def run(make, n, per_epoch):
+        m = make()
+        m._per_epoch_calls = per_epoch
+        m.train(n)
+        z, g = m.engine.admm_state() if m._admm else (None, None)
+        return m.engine.get_params(), z, g, m.engine.get_collocation()
+
+    cases = [
+        (lambda: BurgersIdentification(P(), variant="AB-ADMM", data=os.path.join(GOLD, "data", "TwoSin_burgers_shock.npz"), run=False,
+                                       verbose=False, resample="device"), 1012),
+        (lambda: BurgersIdentification(P(), variant="AB-L2", data=os.path.join(GOLD, "data", "Abgrall_burgers_shock.npz"), run=False,
+                                       verbose=False, resample="device"), 40),
+        (lambda: EulerInference(E(), data=os.path.join(GOLD, "data", "Abgrall_eulers.npz"), run=False, verbose=False, resample="device"), 60),
+    ]
+    for make, n in cases:
+        a, b = run(make, n, True), run(make, n, False)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+        if a[1] is not None:
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
 def test_train_step_from_host_feeds_pinned_points():
     import torch
     from pinns_b200.models import PhysicsInformedNN

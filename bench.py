@@ -354,10 +354,10 @@ def run_ours(args, rank, world, local_rank):
     warm = max(args.warmup, 3)
     for _ in range(warm):
         stepper.adam_step()
+    sampler = ClockSampler(local_rank)   # (NVML initialisation takes tens of ms and differs from rank to rank: before the barrier,
+    eng.kernel_timing(True)              #  or the ranks enter the timed region skewed and the first exchange waits it out)
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
-    eng.kernel_timing(True)
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -201,10 +201,10 @@ def test_fused_and_generic_kernels_agree_at_scale():
     assert rel_err(outs[0][1], outs[1][1]) <= TOL
 
 
-def test_linearity_over_shards_at_full_size():
+@pytest.mark.parametrize("n", [1 << 22, 1 << 26], ids=["4Mi", "64Mi-BASELINE-config-4"])
+def test_linearity_over_shards_at_full_size(n):
     """size-independent property at bench scale: grad(all points) = grad(shard A) + grad(shard B) with job-wide 1/N_f"""
     c = make_case(tg.PDE_BURGERS, B20, tg.LOSS_V4, 100, 64, seed=12)
-    n = 1 << 22
     eng = make_engine(c)
     eng.set_data_weight(0.0)
     eng.sample_collocation(1234, 0, n, n)
@@ -224,6 +224,33 @@ def test_linearity_over_shards_at_full_size():
     l_s, g_s = eng.loss_grad()
     ref = tg.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], Xs)
     assert abs(l_s - ref.loss) <= TOL * abs(ref.loss) and rel_err(g_s, ref.grad) <= TOL
+
+
+def test_tensor_path_linearity_over_shards_at_config5_size():
+    """BASELINE config 5 at its full size ([2,128x8,1], 16 Mi points, tcgen05 path): the same shard-additivity, within the
+    tensor path's stated 5e-5; plus the oracle on a sample of the same Philox stream."""
+    layers = [2] + [128] * 8 + [1]
+    c = make_case(tg.PDE_BURGERS, layers, tg.LOSS_V4, 100, 64, seed=13)
+    n = 1 << 24
+    eng = make_engine(c, path="tensor")
+    eng.set_data_weight(0.0)
+    eng.sample_collocation(1234, 0, n, n)
+    assert eng.kernel_path == "tensor"
+    l_all, g_all = eng.loss_grad()
+    na = n // 3 + 5
+    eng.sample_collocation(1234, 0, na, n)
+    l_a, g_a = eng.loss_grad()
+    eng.sample_collocation(1234, na, n - na, n)
+    l_b, g_b = eng.loss_grad()
+    assert abs((l_a + l_b) - l_all) <= 5e-6 * abs(l_all)
+    assert rel_err(g_a + g_b, g_all) <= 2e-5
+    ns = 8192
+    Xs = sample_collocation(1234, 0, ns, c["prob"].lb, c["prob"].ub).astype(np.float64)
+    eng.set_data_weight(1.0)
+    eng.sample_collocation(1234, 0, ns, ns)
+    l_s, g_s = eng.loss_grad()
+    ref = tg.evaluate(c["theta"], c["prob"], c["X_u"], c["u"], Xs)
+    assert abs(l_s - ref.loss) <= 5e-5 * abs(ref.loss) and rel_err(g_s, ref.grad) <= 5e-5
 
 
 def test_trainable_lambda_adam_moves_lambda_like_the_oracle():

@@ -226,12 +226,13 @@ def test_linearity_over_shards_at_full_size(n):
     assert abs(l_s - ref.loss) <= TOL * abs(ref.loss) and rel_err(g_s, ref.grad) <= TOL
 
 
-def test_tensor_path_linearity_over_shards_at_config5_size():
-    """BASELINE config 5 at its full size ([2,128x8,1], 16 Mi points, tcgen05 path): the same shard-additivity, within the
-    tensor path's stated 5e-5; plus the oracle on a sample of the same Philox stream."""
-    layers = [2] + [128] * 8 + [1]
-    c = make_case(tg.PDE_BURGERS, layers, tg.LOSS_V4, 100, 64, seed=13)
-    n = 1 << 24
+@pytest.mark.parametrize("pde,layers,loss,n", [(tg.PDE_BURGERS, [2] + [128] * 8 + [1], tg.LOSS_V4, 1 << 24),
+                                               (tg.PDE_EULER, [2] + [200] * 5 + [3], tg.LOSS_EULER_MSE, 1 << 20)],
+                         ids=["config5-128x8-16Mi", "euler-200x5-1Mi"])
+def test_tensor_path_linearity_over_shards_at_config5_size(pde, layers, loss, n):
+    """BASELINE config 5 at its full size ([2,128x8,1], 16 Mi points, tcgen05 path) and the reference's Euler net at 1 Mi points: the
+    same shard-additivity, within the tensor path's stated 5e-5; plus the oracle on a sample of the same Philox stream."""
+    c = make_case(pde, layers, loss, 100, 64, seed=13)
     eng = make_engine(c, path="tensor")
     eng.set_data_weight(0.0)
     eng.sample_collocation(1234, 0, n, n)

@@ -98,6 +98,26 @@ def test_tensor_core_path_parity(name, pde, n, nl, loss, n_f):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("knob,value", [("PINN_TC_OVL", "3"), ("PINN_TC_OVL", "0"), ("PINN_TC_FWD2", "0")],
+                         ids=["pipelined-reverse-sweep", "serial-units", "unsplit-forward"])
+@pytest.mark.parametrize("name,pde,n,nl,loss,n_f", [c for c in TENSOR_CASES if c[0] in ("tc-64", "tc-128-admm", "tc-euler-admm-64")],
+                         ids=["tc-64", "tc-128-admm", "tc-euler-admm-64"])
+def test_tensor_core_path_alternative_schedules(name, pde, n, nl, loss, n_f, knob, value, monkeypatch):
+    """The schedules kept behind measurement knobs (pipelined reverse sweep with two TMEM regions, strictly serial
+    units, the forward sweep as one unit per layer) hold the same parity bound as the default one."""
+    monkeypatch.setenv(knob, value)
+    layers = [2] + [n] * nl + [1 if pde == B else 3]
+    case = make_case(pde, layers, loss, 50, n_f, seed=zlib.crc32(name.encode()) % 1000)
+    ref = tg.evaluate(case["theta"], case["prob"], case["X_u"], case["u"], case["X_f"], case["z"], case["gamma"])
+    eng = make_engine(case, path="tensor")
+    loss_gpu, grad = eng.loss_grad()
+    assert abs(loss_gpu - ref.loss) <= TOL_TENSOR * abs(ref.loss)
+    assert rel_err(grad[:eng.num_params], ref.grad) <= TOL_TENSOR
+    l2, g2 = eng.loss_grad()
+    assert np.array_equal(grad, g2) and l2 == loss_gpu
+
+
+@pytest.mark.gpu
 def test_auto_picks_tensor_cores_for_wide_nets_at_scale_and_agrees_with_generic():
     layers = [2] + [128] * 8 + [1]
     case = make_case(tg.PDE_BURGERS, layers, tg.LOSS_V4, 50, 64, seed=77)

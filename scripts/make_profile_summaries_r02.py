@@ -92,7 +92,7 @@ summarise('gpurun_out/prof_small_r02.ncu-rep', 'ncu --set full --clock-control n
 
 # ---- static SASS opcode histograms of every kernel of the library (cuobjdump, no GPU needed) ----
 out = ["# cuobjdump -sass of pinns_b200/csrc/*.o (sm_100a): static opcode histogram per kernel.  Blackwell-native evidence: UTCHMMA = tcgen05.mma,",
-       "# LDTM / STTM = tcgen05.ld / st, UTMALDG = cp.async.bulk.tensor (TMA tensor copy), UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier, UTCBAR = tcgen05.commit, FFMA2 = fma.rn.f32x2."]
+       "# LDTM / STTM = tcgen05.ld / st, UTMALDG = cp.async.bulk.tensor (TMA tensor copy), UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier, UTCBAR = tcgen05.commit, FFMA2 = fma.rn.f32x2, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents."]
 for obj in sorted(os.listdir('pinns_b200/csrc')):
     if not obj.endswith('.o'):
         continue
@@ -111,7 +111,7 @@ for obj in sorted(os.listdir('pinns_b200/csrc')):
             op = p[1] if p[0].startswith('@') and len(p) > 1 else p[0]
             hist[cur][op.split('.')[0]] += 1
     for k, c in hist.items():
-        key = ['UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'UBLKCP', 'UTCBAR', 'SYNCS', 'FFMA2', 'FFMA', 'LDS', 'STS', 'LDG', 'STG', 'LDGSTS', 'RED', 'MUFU', 'SHFL', 'CCTL', 'BAR']
+        key = ['UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'UBLKCP', 'UTCBAR', 'SYNCS', 'FFMA2', 'FFMA', 'LDS', 'STS', 'LDG', 'STG', 'LDGSTS', 'RED', 'MUFU', 'SHFL', 'CCTL', 'BAR', 'ACQBULK', 'PREEXIT']
         out.append("%-14s %-58s total %5d | %s" % (obj, k[:58], sum(c.values()), ' '.join('%s:%d' % (o, c[o]) for o in key if c.get(o))))
 open('profiles/r02_sass_opcodes.txt', 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out))

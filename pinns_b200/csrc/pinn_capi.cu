@@ -72,6 +72,14 @@ struct pinn_handle_s {
   // host feed in flight (pinn_feed_collocation): chunk c = points [feed_first[c], feed_first[c+1]) has landed in
   // d_Xf_owned once feed_ev[c] fires on copy_stream
   cudaStream_t copy_stream = nullptr;
+  // pinn_set_collocation from host memory: small batches (the reference's per-epoch resampling: 8 KB) go through a ring of pinned
+  // staging buffers, so the copy is asynchronous and the host prepares batch k+1 while the GPU works on batch k (a copy from
+  // pageable memory makes the driver wait for the stream first)
+  static constexpr int STAGE_SLOTS = 4;
+  static constexpr size_t STAGE_BYTES = 256 * 1024;
+  float* stage[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned stage_next = 0;
   cudaEvent_t feed_start = nullptr;
   std::vector<cudaEvent_t> feed_ev;
   std::vector<int64_t> feed_first;
@@ -469,6 +477,10 @@ int pinn_destroy(pinn_handle_t h) {
     cudaEventDestroy(h->feed_start);
   }
   for (cudaEvent_t e : h->feed_ev) cudaEventDestroy(e);
+  for (int k = 0; k < pinn_handle_s::STAGE_SLOTS; ++k) {
+    if (h->stage_ev[k]) cudaEventDestroy(h->stage_ev[k]);
+    if (h->stage[k]) cudaFreeHost(h->stage[k]);
+  }
   pinn_comm_detach(h);
   if (h->comm.own) cudaFree(h->comm.own);
   if (h->comm.h_hang) cudaFreeHost(h->comm.h_hang);
@@ -635,7 +647,22 @@ int pinn_set_collocation(pinn_handle_t h, const float* X_f, int64_t n_f, int64_t
   } else {
     int rc = ensure_xf_owned(h, n_f);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_Xf_owned, X_f, (size_t)n_f * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const size_t bytes = (size_t)n_f * 2 * sizeof(float);
+    if (bytes <= pinn_handle_s::STAGE_BYTES) {
+      const int slot = (int)(h->stage_next++ % pinn_handle_s::STAGE_SLOTS);
+      if (!h->stage[slot]) {
+        CK(cudaHostAlloc(&h->stage[slot], pinn_handle_s::STAGE_BYTES, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&h->stage_ev[slot], cudaEventDisableTiming));
+      } else {
+        CK(cudaEventSynchronize(h->stage_ev[slot]));  // the copy that last used this slot (four batches ago) has left it
+      }
+      memcpy(h->stage[slot], X_f, bytes);               // the caller's buffer is free again when this call returns
+      CK(cudaMemcpyAsync(h->d_Xf_owned, h->stage[slot], bytes, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaEventRecord(h->stage_ev[slot], h->stream));
+    } else {
+      // pageable source: the runtime stages the data before it returns (and waits for the stream to do so)
+      CK(cudaMemcpyAsync(h->d_Xf_owned, X_f, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     h->d_Xf = h->d_Xf_owned;
   }
   h->n_f = n_f;

@@ -161,7 +161,8 @@ class Engine:
             n = Xf.shape[0]
             self._ck(capi.lib.pinn_set_collocation(self._h, Xf.ctypes.data_as(C.c_void_p), n, int(nf_global), 0),
                      "pinn_set_collocation")
-            self.synchronize()  # Xf is a temporary
+            # (host memory has been consumed when the call returns: small batches are copied into a pinned staging ring of the
+            #  handle, larger ones staged by the runtime -- no synchronisation, the host prepares the next batch meanwhile)
         self.n_f = int(n)
 
     def set_collocation_ptr(self, ptr: int, n_f: int, nf_global: int = 0, on_device: bool = True):

@@ -192,7 +192,8 @@ int pinn_admm_adam_step(pinn_handle_t h, int inf_admm_quirk);
  * `pending` says whether a z/gamma update is still owed on entry (it is folded into the first Adam step's pass) and, with
  * admm = 1, one is owed again on return (the caller folds it into its next step or flushes it with pinn_admm_update).
  * Same launches, same bits as the calls above made one by one: at the reference's batch sizes an epoch is ~25 us of GPU work
- * and the per-call host overhead of an interpreted loop was as much again.                                        */
+ * and the per-call host overhead of an interpreted loop was as much again.  Single-GPU loops only (a data-parallel rank
+ * samples its own counter range and the ranks are summed every step: distributed.DataParallelStepper).                */
 int pinn_resampled_epochs(pinn_handle_t h, int64_t n_epochs, int admm, int pending, uint64_t seed, uint64_t first_batch,
                           int64_t n_f, int64_t nf_global);
 int pinn_admm_get_state(pinn_handle_t h, float* z, float* gamma, int on_device); /* [N_f, n_res] each */

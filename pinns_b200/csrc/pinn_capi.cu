@@ -1151,6 +1151,9 @@ int pinn_resampled_epochs(pinn_handle_t h, int64_t n_epochs, int admm, int pendi
   if (!h || n_epochs < 0 || n_f <= 0) return PINN_E_INVALID;
   REQUIRE(!admm || h->cfg.loss == PINN_LOSS_V5_ADMM || h->cfg.loss == PINN_LOSS_V2_INF_ADMM, PINN_E_STATE,
           "pinn_resampled_epochs: admm = 1 but the loss is not an ADMM loss");
+  // the batches are drawn for the whole job: a data-parallel rank samples its own counter range and sums over ranks between
+  // the pass and the update (distributed.DataParallelStepper), which this single-handle loop does not do
+  REQUIRE(!(h->comm.attached && h->comm.world > 1), PINN_E_STATE, "pinn_resampled_epochs: not for handles of a data-parallel group");
   for (int64_t k = 0; k < n_epochs; ++k) {
     int rc = pending ? pinn_admm_adam_step(h, 0) : pinn_adam_steps(h, 1);
     if (rc) return rc;

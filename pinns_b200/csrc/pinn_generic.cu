@@ -180,7 +180,13 @@ __device__ __forceinline__ StreamsT<S> layer_inputs_T(const GenParams& g, float*
   return r;
 }
 
-// one stream's operands -> buf: Hs [T][np_in + 4] | Zs [T][np_out + 4]   (asynchronous)
+// 16-byte chunk c of a Z-bar row sits at chunk position zswz(c): the weight-gradient threads of a warp read the two chunks of
+// their 8 columns, 2 jg and 2 jg + 1 for up to 25 consecutive jg; unswizzled those are the even (odd) positions only = 4 of
+// the 8 bank groups, ~7 wavefronts per LDS.128; with bit 0 flipped in every other group of eight, 8 consecutive jg cover all
+// 8 groups: 4 wavefronts, the minimum for 25 distinct chunks (the step was bound by the LSU, not by its FFMA2)
+__device__ __forceinline__ int zswz(int c) { return c ^ ((c >> 3) & 1); }
+
+// one stream's operands -> buf: Hs [T][np_in + 4] | Zs [T][np_out + 4] (chunks at zswz)   (asynchronous)
 __device__ __forceinline__ void stage_wg(float* buf, const float* hsrc, int ld_h, int np_in, const float* zsrc, int ld_z,
                                          int np_out) {
   const int ldh = np_in + 4, ldz = np_out + 4;
@@ -189,7 +195,7 @@ __device__ __forceinline__ void stage_wg(float* buf, const float* hsrc, int ld_h
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int p = warp; p < T; p += nwarps) {
     for (int c = lane; c < np_in / 4; c += 32) cp_async16(Hs + p * ldh + c * 4, hsrc + (size_t)p * ld_h + c * 4);
-    for (int c = lane; c < np_out / 4; c += 32) cp_async16(Zs + p * ldz + c * 4, zsrc + (size_t)p * ld_z + c * 4);
+    for (int c = lane; c < np_out / 4; c += 32) cp_async16(Zs + p * ldz + zswz(c) * 4, zsrc + (size_t)p * ld_z + c * 4);
   }
 }
 
@@ -237,8 +243,8 @@ __device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const fl
       for (int p = 0; p < T; ++p) {
         const float4 h0 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8);
         const float4 h1 = *reinterpret_cast<const float4*>(Hs + p * ldh + ig * 8 + 4);
-        const float4 z0 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8);
-        const float4 z1 = *reinterpret_cast<const float4*>(Zs + p * ldz + jg * 8 + 4);
+        const float4 z0 = *reinterpret_cast<const float4*>(Zs + p * ldz + zswz(2 * jg) * 4);
+        const float4 z1 = *reinterpret_cast<const float4*>(Zs + p * ldz + zswz(2 * jg + 1) * 4);
         const float h[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const float2 z[4] = {make_float2(z0.x, z0.y), make_float2(z0.z, z0.w), make_float2(z1.x, z1.y), make_float2(z1.z, z1.w)};
 #pragma unroll
@@ -269,7 +275,7 @@ __device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const fl
       for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
         float sum = 0.f;
 #pragma unroll 8
-        for (int p = 0; p < T; ++p) sum += Zs[p * ldz + j];
+        for (int p = 0; p < T; ++p) sum += Zs[p * ldz + zswz(j >> 2) * 4 + (j & 3)];
         gb[j] = first ? sum : gb[j] + sum;
       }
     }

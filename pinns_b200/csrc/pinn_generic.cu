@@ -17,7 +17,13 @@
 namespace {
 
 constexpr int T = PINN_TILE;
+// Threads per CTA: 8 warps (two CTAs per SM at large N), or 9 where the ninth warp saves a whole round of the F / B GEMMs: a
+// warp owns one 8-neuron output group per round, and the reference's width 200 is 25 groups -- 8 warps need 4 rounds (8, 8, 8, 1),
+// a cluster of 3 CTAs two (24, 1); with 9 warps it is 3 rounds, or one.  Measured: Euler [2,200x5,3] at 1000 points 289 -> 257 us
+// per Adam step, [2,200x8,1] 610 -> 527 us; for nets whose round count does not change 9 warps only cost the second CTA per SM
+// ([2,128x8,1] at 65 536 points 6.5 -> 8.3 ms), so the choice is made per net (gen_threads_for).
 constexpr int GEN_THREADS = 256;
+constexpr int GEN_THREADS_WIDE = 288;
 
 // A 32-point tile is owned by a cluster of `cs` CTAs (cs = 1 at large N; up to 8 when the job has fewer tiles than the
 // GPU has CTA slots, e.g. the reference's N_f = 1000 batches of a 200-wide net = 32 tiles): the CTAs split the output
@@ -706,16 +712,16 @@ __device__ __forceinline__ void generic_body(const GenParams& g, int bid, int nb
   }
 }
 
-template <int S>
-__global__ void __launch_bounds__(GEN_THREADS, 2) pinn_generic_kernel(const __grid_constant__ GenParams g) {
+template <int S, int NT>
+__global__ void __launch_bounds__(NT, NT > 256 ? 1 : 2) pinn_generic_kernel(const __grid_constant__ GenParams g) {
   extern __shared__ float smem[];
   generic_body<S>(g, blockIdx.x, gridDim.x, smem);
 }
 
 // residual tiles (CTAs [0, grid_res)) and data-term tiles (the rest) in one launch: at the reference's batch sizes
 // neither job fills the GPU, and one launch + one partial-sum reduction replaces two of each
-template <int S>
-__global__ void __launch_bounds__(GEN_THREADS, 2)
+template <int S, int NT>
+__global__ void __launch_bounds__(NT, NT > 256 ? 1 : 2)
     pinn_generic_dual_kernel(const __grid_constant__ GenParams g, const __grid_constant__ GenParams gd, int grid_res) {
   extern __shared__ float smem[];
   if ((int)blockIdx.x < grid_res) generic_body<S>(g, blockIdx.x, grid_res, smem);
@@ -738,12 +744,29 @@ extern "C" int pinn_debug_trace(long long* out, int* n) {
 // shared memory of one CTA: act [S][kch][T] + max(weight slices [warps][kch][8], nbuf weight-gradient staging buffers
 // [T][2 npmax + 8]).  kch covers the widest layer unless that would pass ~216 KB; the staging is double buffered when it
 // fits and (small grids) occupancy is not at stake
-size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out) {
+// 288 threads iff the ninth warp lowers the number of GEMM rounds of the widest layer for some cluster size the launcher uses
+// (see GEN_THREADS_WIDE) and the net is too wide for two CTAs per SM anyway.  A property of the NET, not of the launch: the
+// forward-only passes (z / gamma updates, predict) and the training pass of a handle must run the same instantiation -- the
+// folded ADMM update is bit-identical to the two-pass form only if both evaluate the residuals with the same machine code.
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out, int threads);
+static int gen_threads_for(const NetDesc& net, int S) {
+  int groups = 1;
+  for (int l = 1; l <= net.L; ++l) groups = net.np[l] / 8 > groups ? net.np[l] / 8 : groups;
+  bool fewer = false;
+  for (int cs = 1; cs <= 4; ++cs) {
+    auto rounds = [&](int warps) { return (groups + cs * warps - 1) / (cs * warps); };
+    fewer = fewer || rounds(GEN_THREADS_WIDE / 32) < rounds(GEN_THREADS / 32);
+  }
+  const bool one_cta_per_sm = pinn_generic_smem_bytes(net, S > 1 ? S : 3, true, nullptr, nullptr, GEN_THREADS) > 113 * 1024;
+  return (fewer && one_cta_per_sm) ? GEN_THREADS_WIDE : GEN_THREADS;
+}
+
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out, int threads) {
   const size_t gsz = (size_t)T * (2 * net.npmax + 8);
   const size_t budget = 216 * 1024 / sizeof(float);
   int kch = net.npmax;
   auto total = [&](int k, int nbuf) {
-    const size_t w = (size_t)(GEN_THREADS / 32) * k * 8;
+    const size_t w = (size_t)(threads / 32) * k * 8;
     return (size_t)S * k * T + (w > nbuf * gsz ? w : nbuf * gsz);
   };
   while (kch > 8 && total(kch, 1) > budget) kch -= 8;
@@ -757,11 +780,12 @@ size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, i
 
 cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStream_t stream) {
   GenParams g = g_in;
-  const size_t smem = pinn_generic_smem_bytes(g.net, S, grid > 148, &g.kch, &g.wg_nbuf);
+  const int nt = gen_threads_for(g.net, S);
+  const size_t smem = pinn_generic_smem_bytes(g.net, S, grid > 148, &g.kch, &g.wg_nbuf, nt);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.blockDim = dim3(nt);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -772,17 +796,27 @@ cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStre
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
-#define LAUNCH(SS)                                                                                              \
-  e = cudaFuncSetAttribute(pinn_generic_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-  if (e != cudaSuccess) return e;                                                                               \
-  e = cudaLaunchKernelEx(&cfg, pinn_generic_kernel<SS>, g);                                                     \
+#define LAUNCH(SS, NT)                                                                                              \
+  e = cudaFuncSetAttribute(pinn_generic_kernel<SS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+  if (e != cudaSuccess) return e;                                                                                   \
+  e = cudaLaunchKernelEx(&cfg, pinn_generic_kernel<SS, NT>, g);                                                     \
   if (e != cudaSuccess) return e;
-  if (S == 1) {
-    LAUNCH(1)
-  } else if (S == 3) {
-    LAUNCH(3)
+  if (nt == GEN_THREADS) {
+    if (S == 1) {
+      LAUNCH(1, GEN_THREADS)
+    } else if (S == 3) {
+      LAUNCH(3, GEN_THREADS)
+    } else {
+      LAUNCH(4, GEN_THREADS)
+    }
   } else {
-    LAUNCH(4)
+    if (S == 1) {
+      LAUNCH(1, GEN_THREADS_WIDE)
+    } else if (S == 3) {
+      LAUNCH(3, GEN_THREADS_WIDE)
+    } else {
+      LAUNCH(4, GEN_THREADS_WIDE)
+    }
   }
 #undef LAUNCH
   return cudaGetLastError();
@@ -792,14 +826,15 @@ cudaError_t pinn_generic_launch(const GenParams& g_in, int S, int grid, cudaStre
 cudaError_t pinn_generic_dual_launch(const GenParams& g_in, int S, int grid_res, const GenParams& gd_in, int grid_data,
                                      cudaStream_t stream) {
   GenParams g = g_in, gd = gd_in;
-  const size_t smem_res = pinn_generic_smem_bytes(g.net, S, grid_res + grid_data > 148, &g.kch, &g.wg_nbuf);
-  const size_t smem_data = pinn_generic_smem_bytes(gd.net, 1, true, &gd.kch, &gd.wg_nbuf);
+  const int nt = gen_threads_for(g.net, S);
+  const size_t smem_res = pinn_generic_smem_bytes(g.net, S, grid_res + grid_data > 148, &g.kch, &g.wg_nbuf, nt);
+  const size_t smem_data = pinn_generic_smem_bytes(gd.net, 1, true, &gd.kch, &gd.wg_nbuf, nt);
   const size_t smem = smem_res > smem_data ? smem_res : smem_data;
   gd.cluster = g.cluster;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid_res + grid_data);
-  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.blockDim = dim3(nt);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -810,15 +845,23 @@ cudaError_t pinn_generic_dual_launch(const GenParams& g_in, int S, int grid_res,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
-#define LAUNCH(SS)                                                                                                  \
-  e = cudaFuncSetAttribute(pinn_generic_dual_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-  if (e != cudaSuccess) return e;                                                                                   \
-  e = cudaLaunchKernelEx(&cfg, pinn_generic_dual_kernel<SS>, g, gd, grid_res);                                      \
+#define LAUNCH(SS, NT)                                                                                                  \
+  e = cudaFuncSetAttribute(pinn_generic_dual_kernel<SS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+  if (e != cudaSuccess) return e;                                                                                       \
+  e = cudaLaunchKernelEx(&cfg, pinn_generic_dual_kernel<SS, NT>, g, gd, grid_res);                                      \
   if (e != cudaSuccess) return e;
-  if (S == 3) {
-    LAUNCH(3)
+  if (nt == GEN_THREADS) {
+    if (S == 3) {
+      LAUNCH(3, GEN_THREADS)
+    } else {
+      LAUNCH(4, GEN_THREADS)
+    }
   } else {
-    LAUNCH(4)
+    if (S == 3) {
+      LAUNCH(3, GEN_THREADS_WIDE)
+    } else {
+      LAUNCH(4, GEN_THREADS_WIDE)
+    }
   }
 #undef LAUNCH
   return cudaGetLastError();
@@ -840,12 +883,12 @@ int pinn_generic_cluster_capacity(int cs) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaFuncSetAttribute(pinn_generic_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(pinn_generic_kernel<3, GEN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, pinn_generic_kernel<3>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, pinn_generic_kernel<3, GEN_THREADS>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }

@@ -45,7 +45,7 @@ struct GenParams {
   int wg_nbuf;          // weight-gradient staging buffers (1 or 2; set by pinn_generic_launch)
 };
 
-size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out);
+size_t pinn_generic_smem_bytes(const NetDesc& net, int S, bool want_occupancy, int* kch_out, int* nbuf_out, int threads = 256);
 cudaError_t pinn_generic_launch(const GenParams& g, int S, int grid, cudaStream_t stream);
 int pinn_generic_cluster_capacity(int cs);  // clusters of cs CTAs resident at one CTA per SM (0: unknown)
 cudaError_t pinn_generic_dual_launch(const GenParams& g, int S, int grid_res, const GenParams& gd, int grid_data,

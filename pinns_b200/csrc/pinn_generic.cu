@@ -228,8 +228,10 @@ __device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const fl
     float* buf = smem + (nbuf == 2 ? (s & 1) * bufsz : 0);
     const float* Hs = buf;
     const float* Zs = buf + T * ldh;
+    TRACE(210 + s);
     cp_async_wait_all();
     __syncthreads();  // stream s landed; every thread is past stream s-1, whose buffer may be refilled
+    TRACE(220 + s);
     if (nbuf == 2 && s + 1 < S)
       stage_wg(smem + ((s + 1) & 1) * bufsz, hin.p[s + 1], hin.ld, np_in, zbT + (size_t)(s + 1) * T * ld_z, ld_z, np_out);
     // fewer 8x8 tiles than threads in the cluster (625 for 200 x 200 at the reference's batch sizes): every rank takes a
@@ -260,6 +262,7 @@ __device__ void weight_grad(const GenParams& g, const StreamsT<S>& hin, const fl
           for (int b = 0; b < 4; ++b) acc[a][b] = ffma2(hh, z[b], acc[a][b]);
         }
       }
+      TRACE(230 + s);
       if (one_task && s < S - 1) continue;  // keep accumulating over the streams in registers
       // the partial row starts at zero: plain stores on the first visit, else one batch of 8 loads per row
       const bool plain = first && (one_task || s == 0);

@@ -15,7 +15,7 @@ PINN_B200_LIB=$PWD/scripts/variants/libpinn_sktrace.so python scripts/small_trac
 python -m pytest tests -m gpu -q -s --timeout 900 > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest_gpu.log
 # ---- under ncu (never a bench value) ----
 B="python bench.py --steps 2 --warmup 3 --nf-global 8388608 --nf-wide 262144 --cpu-points 65536"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/r02_ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/r02_ncu_launch.log 2>&1
 T="python scripts/tensor_bench.py 128 75776"
 ncu --set full --clock-control none --import-source on -k regex:pinn_tc_kernel -s 2 -c 1 -o gpurun_out/prof_tensor_r02 -f $T > gpurun_out/r02_ncu_tensor.log 2>&1
 Q="python scripts/quick_bench.py 2097152"
